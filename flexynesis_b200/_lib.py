@@ -1,0 +1,267 @@
+"""ctypes binding of libfxn_b200.so (the C ABI declared in include/flexynesis_b200.h).
+
+There is no fallback: if the shared library is missing the import of the engine fails with instructions, and
+every wrapper raises on a non-zero return code with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfxn_b200.so")
+
+c_f32p = C.c_void_p
+c_ll = C.c_longlong
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("lda", c_ll), ("a_mn_major", C.c_int),
+        ("b_hi", C.c_void_p), ("b_lo", C.c_void_p), ("ldb", c_ll), ("b_mn_major", C.c_int),
+        ("nterms", C.c_int),
+        ("C", C.c_void_p), ("ldc", c_ll),
+        ("bias", C.c_void_p),
+        ("c_hi", C.c_void_p), ("c_lo", C.c_void_p), ("ldp", c_ll),
+        ("colstats", C.c_void_p), ("stats_mode", C.c_int),
+        ("splitk", C.c_int), ("block_n", C.c_int),
+        ("epi_act", C.c_int), ("accumulate", C.c_int),
+        ("alpha", C.c_float), ("alpha_dev", C.c_void_p),
+        ("mse_x", C.c_void_p), ("ldx", c_ll), ("mse_acc", C.c_void_p),
+    ]
+
+
+class BnFwdDesc(C.Structure):
+    _fields_ = [
+        ("V", C.c_void_p), ("ldv", c_ll), ("rows", c_ll), ("cols", C.c_int),
+        ("partials", C.c_void_p), ("ntiles", C.c_int), ("tile_rows", C.c_int), ("partials_ld", C.c_int),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+        ("momentum", C.c_float), ("eps", C.c_float),
+        ("train", C.c_int), ("act", C.c_int), ("p_drop", C.c_float),
+        ("mask", C.c_void_p), ("ldm", c_ll), ("seed", C.c_ulonglong), ("seed_dev", C.c_void_p),
+        ("out", C.c_void_p), ("ldo", c_ll),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldp", c_ll),
+        ("saved", C.c_void_p),
+    ]
+
+
+class BnBwdDesc(C.Structure):
+    _fields_ = [
+        ("V", C.c_void_p), ("ldv", c_ll), ("dOut", C.c_void_p), ("ldg", c_ll), ("rows", c_ll), ("cols", C.c_int),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("saved", C.c_void_p),
+        ("act", C.c_int), ("p_drop", C.c_float), ("mask", C.c_void_p), ("ldm", c_ll), ("seed", C.c_ulonglong),
+        ("seed_dev", C.c_void_p),
+        ("pre_act", C.c_int),
+        ("sums", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dbias", C.c_void_p),
+        ("dV", C.c_void_p), ("ldd", c_ll),
+        ("dv_hi", C.c_void_p), ("dv_lo", C.c_void_p), ("ldp", c_ll),
+        ("grad_scale", C.c_float), ("accumulate_affine", C.c_int),
+    ]
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"flexynesis_b200: {LIB_PATH} is missing. Build it with `make` (or `python -c 'import __graft_entry__ as g; "
+            "g.build()'`) from the repository root; there is no CPU or PyTorch fallback for the training path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.fxn_last_error.restype = C.c_char_p
+    lib.fxn_launch_count.restype = c_ll
+    lib.fxn_version.restype = C.c_int
+    return lib
+
+
+lib = _load()
+
+# every exported symbol that include/flexynesis_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "fxn_version", "fxn_last_error", "fxn_launch_count", "fxn_reset_launch_count", "fxn_split_planes", "fxn_gemm",
+    "fxn_gemm_stat_tiles", "fxn_bn_act_fwd", "fxn_bn_act_bwd", "fxn_col_stats", "fxn_head_out_fwd", "fxn_head_out_bwd",
+    "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
+    "fxn_split_planes_multi", "fxn_gather_rows",
+]
+
+
+class FxnError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise FxnError(f"{what or 'libfxn_b200'} failed ({rc}): {lib.fxn_last_error().decode()}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib.fxn_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib.fxn_reset_launch_count()
+
+
+def pad8(n: int) -> int:
+    return (int(n) + 7) // 8 * 8
+
+
+class Planes:
+    """bf16 (hi, lo) operand planes of an fp32 matrix [rows x cols], shared leading dimension ld (elements)."""
+    __slots__ = ("hi", "lo", "rows", "cols", "ld", "off")
+
+    def __init__(self, hi, lo, rows, cols, ld, off=0):
+        self.hi, self.lo, self.rows, self.cols, self.ld, self.off = hi, lo, rows, cols, ld, off
+
+    @staticmethod
+    def empty(rows, cols, device, ld=None):
+        ld = ld or pad8(cols)
+        hi = torch.zeros(rows * ld, dtype=torch.bfloat16, device=device)
+        lo = torch.zeros(rows * ld, dtype=torch.bfloat16, device=device)
+        return Planes(hi, lo, rows, cols, ld)
+
+    def cols_view(self, c0, ncols):
+        """Column window [c0, c0 + ncols) sharing storage (c0 % 8 == 0)."""
+        assert c0 % 8 == 0
+        return Planes(self.hi, self.lo, self.rows, ncols, self.ld, self.off + c0)
+
+    def rows_view(self, r0, nrows):
+        return Planes(self.hi, self.lo, nrows, self.cols, self.ld, self.off + r0 * self.ld)
+
+    @property
+    def hi_ptr(self):
+        return self.hi.data_ptr() + 2 * self.off
+
+    @property
+    def lo_ptr(self):
+        return self.lo.data_ptr() + 2 * self.off
+
+    def to_float(self):
+        h = self.hi[self.off:].float()
+        l = self.lo[self.off:].float()
+        full = (h + l)[: (self.rows - 1) * self.ld + self.cols]
+        out = torch.empty(self.rows, self.cols, device=self.hi.device)
+        for r in range(self.rows):   # debugging helper only
+            out[r] = full[r * self.ld: r * self.ld + self.cols]
+        return out
+
+
+def fptr(t, off=0):
+    """Pointer to element `off` of a float32 tensor."""
+    return None if t is None else t.data_ptr() + 4 * off
+
+
+def split_planes(src: torch.Tensor, dst: Planes) -> None:
+    assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
+    check(lib.fxn_split_planes(C.c_void_p(src.data_ptr()), c_ll(src.stride(0)), c_ll(src.shape[0]), c_ll(src.shape[1]),
+                               C.c_void_p(dst.hi_ptr), C.c_void_p(dst.lo_ptr), c_ll(dst.ld), C.c_void_p(stream())),
+          "fxn_split_planes")
+
+
+def gemm(M, N, K, a: Planes, a_mn, b: Planes, b_mn, *, C_ptr=None, ldc=0, bias=None, out: Planes = None,
+         colstats=None, stats_mode=0, splitk=0, nterms=3, block_n=0, epi_act=0, accumulate=False, alpha=0.0,
+         alpha_dev=None, mse_x=None, ldx=0, mse_acc=None) -> None:
+    d = GemmDesc()
+    d.M, d.N, d.K = int(M), int(N), int(K)
+    d.a_hi, d.a_lo, d.lda, d.a_mn_major = a.hi_ptr, a.lo_ptr, a.ld, int(a_mn)
+    d.b_hi, d.b_lo, d.ldb, d.b_mn_major = b.hi_ptr, b.lo_ptr, b.ld, int(b_mn)
+    d.nterms = nterms
+    d.C, d.ldc = C_ptr, int(ldc)
+    d.bias = bias
+    if out is not None:
+        d.c_hi, d.c_lo, d.ldp = out.hi_ptr, out.lo_ptr, out.ld
+    d.colstats, d.stats_mode = colstats, stats_mode
+    d.splitk, d.block_n = splitk, block_n
+    d.epi_act, d.accumulate = epi_act, int(accumulate)
+    d.alpha, d.alpha_dev = alpha, alpha_dev
+    d.mse_x, d.ldx, d.mse_acc = mse_x, int(ldx), mse_acc
+    check(lib.fxn_gemm(C.byref(d), C.c_void_p(stream())), "fxn_gemm")
+
+
+def stat_tiles(M: int) -> int:
+    return int(lib.fxn_gemm_stat_tiles(int(M)))
+
+
+def col_stats(V_ptr, ldv, rows, cols, tile_rows, partials_ptr) -> None:
+    check(lib.fxn_col_stats(C.c_void_p(V_ptr), c_ll(ldv), c_ll(rows), C.c_int(cols), C.c_int(tile_rows),
+                            C.c_void_p(partials_ptr), C.c_void_p(stream())), "fxn_col_stats")
+
+
+def bn_fwd(**kw) -> None:
+    d = BnFwdDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    check(lib.fxn_bn_act_fwd(C.byref(d), C.c_void_p(stream())), "fxn_bn_act_fwd")
+
+
+def bn_bwd(**kw) -> None:
+    d = BnBwdDesc()
+    for k, v in kw.items():
+        setattr(d, k, v)
+    check(lib.fxn_bn_act_bwd(C.byref(d), C.c_void_p(stream())), "fxn_bn_act_bwd")
+
+
+def head_out_fwd(D, ldd, rows, sh, W, bias, Cc, logits, ldl, kind, y, acc) -> None:
+    check(lib.fxn_head_out_fwd(C.c_void_p(D), c_ll(ldd), C.c_int(rows), C.c_int(sh), C.c_void_p(W), C.c_void_p(bias),
+                               C.c_int(Cc), C.c_void_p(logits), c_ll(ldl), C.c_int(kind), C.c_void_p(y),
+                               C.c_void_p(acc), C.c_void_p(stream())), "fxn_head_out_fwd")
+
+
+def head_out_bwd(D, ldd, rows, sh, W, Cc, logits, ldl, kind, y, acc, coef, weight, dD, ldg, dW, dbias) -> None:
+    check(lib.fxn_head_out_bwd(C.c_void_p(D), c_ll(ldd), C.c_int(rows), C.c_int(sh), C.c_void_p(W), C.c_int(Cc),
+                               C.c_void_p(logits), c_ll(ldl), C.c_int(kind), C.c_void_p(y), C.c_void_p(acc),
+                               C.c_void_p(coef), C.c_void_p(weight), C.c_void_p(dD), c_ll(ldg), C.c_void_p(dW),
+                               C.c_void_p(dbias), C.c_void_p(stream())), "fxn_head_out_bwd")
+
+
+def cox_fwd(o, ldo, durations, events, n, coef, acc) -> None:
+    check(lib.fxn_cox_fwd(C.c_void_p(o), c_ll(ldo), C.c_void_p(durations), C.c_void_p(events), C.c_int(n),
+                          C.c_void_p(coef), C.c_void_p(acc), C.c_void_p(stream())), "fxn_cox_fwd")
+
+
+def total_loss(n, acc, kinds, log_vars, dlog_vars, weighting, out) -> None:
+    check(lib.fxn_total_loss(C.c_int(n), C.c_void_p(acc), C.c_void_p(kinds), C.c_void_p(log_vars),
+                             C.c_void_p(dlog_vars), C.c_int(int(weighting)), C.c_void_p(out), C.c_void_p(stream())),
+          "fxn_total_loss")
+
+
+def triplet_fwd(A, P, N, ld, rows, L, margin, rowloss, acc) -> None:
+    check(lib.fxn_triplet_fwd(C.c_void_p(A), C.c_void_p(P), C.c_void_p(N), c_ll(ld), C.c_int(rows), C.c_int(L),
+                              C.c_float(margin), C.c_void_p(rowloss), C.c_void_p(acc), C.c_void_p(stream())),
+          "fxn_triplet_fwd")
+
+
+def triplet_bwd(A, P, N, ld, rows, L, rowloss, weight, dA, dP, dN, ldg, accumulate_a) -> None:
+    check(lib.fxn_triplet_bwd(C.c_void_p(A), C.c_void_p(P), C.c_void_p(N), c_ll(ld), C.c_int(rows), C.c_int(L),
+                              C.c_void_p(rowloss), C.c_void_p(weight), C.c_void_p(dA), C.c_void_p(dP), C.c_void_p(dN),
+                              c_ll(ldg), C.c_int(int(accumulate_a)), C.c_void_p(stream())), "fxn_triplet_bwd")
+
+
+def clip_adam(params, grads, m, v, n, lr, max_norm, grad_scale, sumsq, step, norm_out, beta1=0.9, beta2=0.999,
+              eps=1e-8) -> None:
+    check(lib.fxn_clip_adam_step(C.c_void_p(params), C.c_void_p(grads), C.c_void_p(m), C.c_void_p(v), c_ll(n),
+                                 C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(max_norm),
+                                 C.c_float(grad_scale), C.c_void_p(sumsq), C.c_void_p(step), C.c_void_p(norm_out),
+                                 C.c_void_p(stream())), "fxn_clip_adam_step")
+
+
+def split_planes_multi(src, segs, nseg, max_elems, hi, lo) -> None:
+    check(lib.fxn_split_planes_multi(C.c_void_p(src), C.c_void_p(segs), C.c_int(nseg), c_ll(max_elems), C.c_void_p(hi),
+                                     C.c_void_p(lo), C.c_void_p(stream())), "fxn_split_planes_multi")
+
+
+def gather_rows(src, ld_src, idx, nrows, cols, out, ldo, planes: "Planes" = None) -> None:
+    check(lib.fxn_gather_rows(C.c_void_p(src), c_ll(ld_src), C.c_void_p(idx), c_ll(nrows), c_ll(cols), C.c_void_p(out),
+                              c_ll(ldo), C.c_void_p(planes.hi_ptr if planes else None),
+                              C.c_void_p(planes.lo_ptr if planes else None), c_ll(planes.ld if planes else 0),
+                              C.c_void_p(stream())), "fxn_gather_rows")

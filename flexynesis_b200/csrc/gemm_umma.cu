@@ -40,9 +40,20 @@ struct GemmKernelArgs {
   float* colstats;        // [m_tiles][2][N]: (sum, M2 about the tile mean); stats_mode 1 = sum only
   int stats_mode;
   int vec_c;              // C rows are 16B aligned -> float4 stores
+  int epi_act;            // 0 none, 1 relu, 3 sigmoid, 6 leaky_relu(0.2); applied after alpha and bias
+  int accumulate;         // C += result
+  float alpha; const float* alpha_dev;
+  const float* mse_x; long long ldx; float* mse_acc;   // fused sigmoid-MSE: see fxn_gemm_desc
 };
 
-__device__ __forceinline__ uint32_t a_plane_bytes() { return BM * BK * 2; }
+__device__ __forceinline__ float epi_activation(float x, int act) {
+  switch (act) {
+    case 1: return fmaxf(x, 0.f);
+    case 3: return 1.f / (1.f + __expf(-x));
+    case 6: return x > 0.f ? x : 0.2f * x;
+    default: return x;
+  }
+}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -174,6 +185,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     const bool add_bias = (p.bias != nullptr) && (blockIdx.z == 0);
+    const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
     for (int c0 = 0; c0 < p.bn; c0 += 32) {
       uint32_t v[32];
       const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
@@ -190,16 +202,22 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       for (int j = 0; j < 32; j += 4) {
         if (j < ncols) {
           float4 o;
-          o.x = __uint_as_float(v[j + 0]);
-          o.y = __uint_as_float(v[j + 1]);
-          o.z = __uint_as_float(v[j + 2]);
-          o.w = __uint_as_float(v[j + 3]);
+          o.x = __uint_as_float(v[j + 0]) * alpha;
+          o.y = __uint_as_float(v[j + 1]) * alpha;
+          o.z = __uint_as_float(v[j + 2]) * alpha;
+          o.w = __uint_as_float(v[j + 3]) * alpha;
           if (add_bias) {
             const int n = n0 + c0 + j;
             if (n + 0 < p.N) o.x += __ldg(p.bias + n + 0);
             if (n + 1 < p.N) o.y += __ldg(p.bias + n + 1);
             if (n + 2 < p.N) o.z += __ldg(p.bias + n + 2);
             if (n + 3 < p.N) o.w += __ldg(p.bias + n + 3);
+          }
+          if (p.epi_act) {
+            o.x = epi_activation(o.x, p.epi_act);
+            o.y = epi_activation(o.y, p.epi_act);
+            o.z = epi_activation(o.z, p.epi_act);
+            o.w = epi_activation(o.w, p.epi_act);
           }
           *reinterpret_cast<float4*>(stg + row * lds + c0 + j) = o;
         }
@@ -218,6 +236,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const float* srow = stg + r * lds;
         if (p.splitk > 1) {
           for (int c = lane; c < ncolsv; c += 32) atomicAdd(crow + c, srow[c]);
+        } else if (p.accumulate) {
+          for (int c = lane; c < ncolsv; c += 32) crow[c] += srow[c];
         } else if (p.vec_c) {
           for (int c = lane * 4; c < ncolsv; c += 128) {
             const float4 o = *reinterpret_cast<const float4*>(srow + c);
@@ -234,13 +254,32 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
       }
     }
+    // ---- fused sigmoid-MSE (Decoder output + reconstruction loss): staged value is x_hat; accumulate
+    //      sum (x_hat - x)^2 and replace the staged tile by G = (x_hat - x) * x_hat * (1 - x_hat) ----
+    if (p.mse_x != nullptr) {
+      float sq = 0.f;
+      for (int r = ew; r < mrows; r += 4) {
+        float* srow = stg + r * lds;
+        const float* xrow = p.mse_x + static_cast<long long>(m0 + r) * p.ldx + n0;
+        for (int c = lane; c < ncolsv; c += 32) {
+          const float xh = srow[c];
+          const float df = xh - __ldg(xrow + c);
+          sq = fmaf(df, df, sq);
+          srow[c] = df * xh * (1.f - xh);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (lane == 0) atomicAdd(p.mse_acc, sq);
+      __syncwarp();
+    }
     // ---- bf16 hi/lo planes of the result (operand of the next GEMM); ldp % 8 == 0, zero-fills to ldp pad ----
     if (p.c_hi != nullptr) {
       for (int r = ew; r < mrows; r += 4) {
         const float* srow = stg + r * lds;
         const long long off = static_cast<long long>(m0 + r) * p.ldp + n0;
         for (int c = lane * 8; c < p.bn; c += 256) {
-          if (n0 + c >= p.ldp) break;
+          if (n0 + c >= ((p.N + 7) & ~7)) break;      // zero-fill only this GEMM's own pad8(N) columns
           __align__(16) __nv_bfloat16 h[8];
           __align__(16) __nv_bfloat16 l[8];
 #pragma unroll
@@ -266,9 +305,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             m2 = fmaf(d, d, m2);
           }
         }
-        float* dst = p.colstats + (static_cast<long long>(blockIdx.y) * 2) * p.N + n0 + c;
-        dst[0] = s;
-        dst[p.N] = m2;
+        if (p.stats_mode == 3) {
+          atomicAdd(p.colstats + n0 + c, s);     // plain column sums into a caller-zeroed [N] vector (bias gradients)
+        } else {
+          float* dst = p.colstats + (static_cast<long long>(blockIdx.y) * 2) * p.N + n0 + c;
+          dst[0] = s;
+          dst[p.N] = m2;
+        }
       }
     }
   }
@@ -356,6 +399,15 @@ extern "C" int fxn_gemm(const fxn_gemm_desc* d, void* stream_) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int kb_total = (d->K + BK - 1) / BK;
   int splitk = d->splitk > 1 ? d->splitk : 1;
+  if (d->splitk < 0) {   // auto: fill the 148 SMs when the output has few tiles and K is long (weight gradients)
+    const int tiles = ((d->M + BM - 1) / BM) * ((d->N + p.bn - 1) / p.bn);
+    splitk = 1;
+    if (tiles < 74 && kb_total >= 8) {
+      splitk = 148 / tiles;
+      if (splitk > kb_total / 4) splitk = kb_total / 4;
+      if (splitk < 1) splitk = 1;
+    }
+  }
   if (splitk > kb_total) splitk = kb_total;
   int kb_per = (kb_total + splitk - 1) / splitk;
   splitk = (kb_total + kb_per - 1) / kb_per;      // no empty splits
@@ -383,6 +435,15 @@ extern "C" int fxn_gemm(const fxn_gemm_desc* d, void* stream_) {
                  (reinterpret_cast<uintptr_t>(d->c_lo) & 15)))
     return set_error(FXN_ERR_ARG, "fxn_gemm: output planes need both pointers, 16B alignment and ldp %% 8 == 0");
   p.vec_c = (d->C && (reinterpret_cast<uintptr_t>(d->C) & 15) == 0 && d->ldc % 4 == 0) ? 1 : 0;
+  p.epi_act = d->epi_act;
+  p.accumulate = d->accumulate;
+  p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+  p.alpha_dev = d->alpha_dev;
+  p.mse_x = d->mse_x; p.ldx = d->ldx; p.mse_acc = d->mse_acc;
+  if (p.mse_x && (!p.mse_acc || splitk > 1 || p.stats_mode))
+    return set_error(FXN_ERR_ARG, "fxn_gemm: fused MSE needs mse_acc and excludes split-K / column stats");
+  if (splitk > 1 && (p.epi_act || p.accumulate))
+    return set_error(FXN_ERR_ARG, "fxn_gemm: split-K excludes epilogue activation / accumulate");
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
@@ -405,6 +466,10 @@ extern "C" int fxn_gemm(const fxn_gemm_desc* d, void* stream_) {
     cudaError_t e = cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
     if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
+  }
+  if (p.stats_mode == 3) {   // plain column sums are accumulated with atomics: zero the target first
+    cudaError_t e = cudaMemsetAsync(d->colstats, 0, sizeof(float) * d->N, stream);
+    if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "colsum memset: %s", cudaGetErrorString(e));
   }
   if (splitk > 1) {
     cudaError_t e = cudaMemset2DAsync(d->C, d->ldc * sizeof(float), 0, d->N * sizeof(float), d->M, stream);

@@ -1,0 +1,554 @@
+"""Hand-scheduled forward + backward + clip/Adam of the flexynesis models on the B200 kernels (libfxn_b200.so).
+
+The engine does not use autograd: each model family has an explicit kernel schedule (SURVEY.md Appendix A is the
+math spec). All trainable tensors of a model are re-homed as views into one flat fp32 arena (same layout for grads and
+the Adam moments), every Linear weight additionally has bf16 (hi, lo) operand planes that are refreshed in one launch
+after each optimizer step, and all activations live in a per-batch-size workspace so that a whole step can be captured
+in a CUDA graph and replayed.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from ._lib import Planes, fptr, pad8
+
+MOMENTUM, EPS = 0.1, 1e-5
+
+
+def pad128(n: int) -> int:
+    return (int(n) + 127) // 128 * 128
+
+
+# ----------------------------------------------------------------------------------------------------
+# flat parameter arena
+# ----------------------------------------------------------------------------------------------------
+class ParamArena:
+    """Re-homes the parameters of `module` into one flat fp32 buffer; grads / exp_avg / exp_avg_sq mirror it."""
+
+    def __init__(self, module: nn.Module, device: torch.device):
+        self.device = device
+        self.names: List[str] = []
+        self.offset: Dict[str, int] = {}
+        self.shape: Dict[str, torch.Size] = {}
+        self.params: Dict[str, nn.Parameter] = {}
+        off = 0
+        for name, p in module.named_parameters():
+            if p.dtype != torch.float32:
+                raise TypeError(f"parameter {name} is {p.dtype}; the engine is fp32")
+            self.names.append(name)
+            self.offset[name] = off
+            self.shape[name] = p.shape
+            self.params[name] = p
+            off += pad8(p.numel())
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step = torch.zeros(1, dtype=torch.int64, device=device)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for name in self.names:
+                p = self.params[name]
+                view = self.view(name)
+                view.copy_(p.detach().to(device))
+                p.data = view                                  # the module now reads/writes the arena
+        self._ptrs = {n: self.params[n].data_ptr() for n in self.names}
+
+    def view(self, name: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        buf = self.flat if buf is None else buf
+        o = self.offset[name]
+        return buf[o:o + self.shape[name].numel()].view(self.shape[name])
+
+    def versions(self):
+        """In-place updates through torch (optimizer.step, load_state_dict) bump these counters."""
+        return tuple(self.params[n]._version for n in self.names)
+
+    def intact(self) -> bool:
+        """False after module.to(...) / load of new tensors re-pointed the parameters away from the arena."""
+        return all(self.params[n].data_ptr() == self._ptrs[n] for n in self.names)
+
+    def p(self, name: str) -> int:
+        return fptr(self.flat, self.offset[name])
+
+    def g(self, name: str) -> int:
+        return fptr(self.grad, self.offset[name])
+
+
+class WeightPlanes:
+    """bf16 (hi, lo) planes of Linear weights, packed in one arena and refreshed by one fxn_split_planes_multi."""
+
+    def __init__(self, arena: ParamArena):
+        self.arena = arena
+        self.segs: List[List[int]] = []
+        self.size = 0
+        self.hi = self.lo = self.table = None
+        self.max_elems = 0
+
+    def reserve(self, rows: int, ld: int) -> int:
+        off = self.size
+        self.size += pad8(rows * ld)
+        return off
+
+    def add_segment(self, pname: str, src_col0: int, rows: int, cols: int, ld_src: int, dst_off: int, ldp: int):
+        self.segs.append([self.arena.offset[pname] + src_col0, rows, cols, ld_src, dst_off, ldp])
+        self.max_elems = max(self.max_elems, rows * ldp)
+
+    def add_matrix(self, pname: str) -> "Planes":
+        rows, cols = self.arena.shape[pname]
+        ld = pad8(cols)
+        off = self.reserve(rows, ld)
+        self.add_segment(pname, 0, rows, cols, cols, off, ld)
+        return ("planes", off, rows, cols, ld)
+
+    def finalize(self):
+        dev = self.arena.device
+        self.hi = torch.zeros(max(self.size, 8), dtype=torch.bfloat16, device=dev)
+        self.lo = torch.zeros_like(self.hi)
+        self.table = torch.tensor(self.segs, dtype=torch.int64, device=dev)
+
+    def planes(self, off: int, rows: int, cols: int, ld: int) -> Planes:
+        return Planes(self.hi, self.lo, rows, cols, ld, off)
+
+    def refresh(self):
+        L.split_planes_multi(self.arena.flat.data_ptr(), self.table.data_ptr(), len(self.segs), self.max_elems,
+                             self.hi.data_ptr(), self.lo.data_ptr())
+
+
+def _bn_ptrs(bn: nn.BatchNorm1d):
+    return dict(running_mean=bn.running_mean.data_ptr(), running_var=bn.running_var.data_ptr(),
+                num_batches_tracked=bn.num_batches_tracked.data_ptr())
+
+
+class InputCache:
+    """Operand planes of input matrices, keyed by (storage pointer, shape, version): a resident dataset that is fed
+    unchanged step after step (full-batch training) is split once."""
+
+    def __init__(self):
+        self.entries = {}
+        self.enabled = True
+
+    def get(self, slot, x: torch.Tensor, dst: Planes) -> None:
+        if not self.enabled:
+            L.split_planes(x, dst)
+            return
+        key = (x.data_ptr(), tuple(x.shape), x._version, getattr(x, "_fxn_tag", None))
+        if self.entries.get(slot) == key:
+            return
+        L.split_planes(x, dst)
+        self.entries[slot] = key
+
+    def invalidate(self):
+        self.entries.clear()
+
+
+# ----------------------------------------------------------------------------------------------------
+# supervisor heads + losses (shared by every model family)
+# ----------------------------------------------------------------------------------------------------
+class HeadsBlock:
+    """All supervisor MLPs of a model: one concatenated layer_1 GEMM over padded per-variable slots, per-variable
+    BatchNorm/ReLU/Dropout, CUDA-core output layers fused with their loss, Cox by a sort+scan kernel, and the
+    uncertainty-weighted total. Extra (non-head) losses such as mmd_loss / triplet_loss occupy leading slots of the
+    loss table so that the dictionary order of the reference's `losses` is kept."""
+
+    def __init__(self, eng, model, extra_first: Sequence[str] = ()):
+        self.eng = eng
+        a, wp = eng.arena, eng.wplanes
+        self.vars: List[str] = list(model.variables)
+        self.L = eng.latent
+        self.Lp = pad8(self.L)
+        self.kinds, self.C, self.sh = {}, {}, 0
+        self.surv_event, self.surv_time = model.surv_event_var, model.surv_time_var
+        for v in self.vars:
+            mlp = model.MLPs[v]
+            self.C[v] = mlp.layer_out.out_features
+            self.sh = mlp.layer_1.out_features
+            if v == self.surv_event:
+                self.kinds[v] = 3
+            else:
+                self.kinds[v] = 1 if model.variable_types[v] == "numerical" else 2
+        self.shp = pad8(self.sh) if self.vars else 0
+        self.width = len(self.vars) * self.shp
+        # concatenated layer_1 weight planes [nv*shp x Lp]; padded rows stay zero
+        self.w1_off = wp.reserve(max(self.width, 1), self.Lp)
+        for i, v in enumerate(self.vars):
+            wp.add_segment(f"MLPs.{v}.layer_1.weight", 0, self.sh, self.L, self.L, self.w1_off + i * self.shp * self.Lp,
+                           self.Lp)
+        # loss table
+        # extra_first: (name, kind) pairs; kind 1 = (sum, count) accumulator, 3 = value
+        self.loss_names = [n for n, _ in extra_first] + self.vars
+        self.n_losses = len(self.loss_names)
+        dev = eng.device
+        kinds = [k for _, k in extra_first] + [3 if self.kinds[v] == 3 else 1 for v in self.vars]
+        self.kinds_dev = torch.tensor(kinds or [1], dtype=torch.int32, device=dev)
+        self.weighting = bool(model.use_loss_weighting) and self.n_losses > 1
+        if self.weighting:
+            lv = [a.p(f"log_vars.{n}") for n in self.loss_names]
+            dlv = [a.g(f"log_vars.{n}") for n in self.loss_names]
+            self.lv_dev = torch.tensor(lv, dtype=torch.int64, device=dev)
+            self.dlv_dev = torch.tensor(dlv, dtype=torch.int64, device=dev)
+        else:
+            self.lv_dev = self.dlv_dev = None
+        # bias of the concatenated layer_1 (gathered each step: tiny) lives in its own buffer
+        self.b1cat = torch.zeros(max(self.width, 1), dtype=torch.float32, device=dev)
+
+    def workspace(self, B: int):
+        dev = self.eng.device
+        ws = {}
+        w = max(self.width, 8)
+        ws["Zh"] = torch.zeros(B, w, device=dev)
+        ws["Dh"] = torch.zeros(B, w, device=dev)
+        ws["dDh"] = torch.zeros(B, w, device=dev)
+        ws["dZh"] = Planes.empty(B, w, dev, ld=w)
+        ws["partials"] = torch.zeros(L.stat_tiles(B) * 2 * w, device=dev)
+        ws["saved"] = torch.zeros(len(self.vars) + 1, 2 * max(self.shp, 1), device=dev)
+        ws["sums"] = torch.zeros(len(self.vars) + 1, 2 * max(self.shp, 1), device=dev)
+        ws["logits"] = {v: torch.zeros(B, self.C[v], device=dev) for v in self.vars}
+        ws["acc"] = torch.zeros(max(self.n_losses, 1), 2, device=dev)
+        ws["out"] = torch.zeros(2 * max(self.n_losses, 1) + 2, device=dev)
+        ws["coef"] = torch.zeros(B, device=dev)
+        return ws
+
+    def w1_planes(self) -> Planes:
+        return self.eng.wplanes.planes(self.w1_off, max(self.width, 1), self.L, self.Lp)
+
+    # ---- forward: F planes [B x L] (fp32 not needed) -> logits + loss accumulators ----
+    def forward(self, ws, Fp: Planes, B: int, y: Dict[str, torch.Tensor], train: bool, masks, with_loss: bool = True):
+        eng, a = self.eng, self.eng.arena
+        if not self.vars:
+            return
+        model = eng.model
+        # gather the layer_1 biases into the concatenated vector (device-to-device copies of sh floats)
+        for i, v in enumerate(self.vars):
+            self.b1cat[i * self.shp:i * self.shp + self.sh].copy_(a.view(f"MLPs.{v}.layer_1.bias"))
+        mt = L.stat_tiles(B)
+        L.gemm(B, self.width, self.L, Fp, 0, self.w1_planes(), 0, C_ptr=ws["Zh"].data_ptr(), ldc=ws["Zh"].stride(0),
+               bias=self.b1cat.data_ptr(), colstats=ws["partials"].data_ptr() if train else None, stats_mode=2)
+        for i, v in enumerate(self.vars):
+            mlp = model.MLPs[v]
+            c0 = i * self.shp
+            mask = None if masks is None else masks.get(f"MLPs.{v}.dropout")
+            L.bn_fwd(V=fptr(ws["Zh"], c0), ldv=ws["Zh"].stride(0), rows=B, cols=self.sh,
+                     partials=fptr(ws["partials"], c0), ntiles=mt, tile_rows=128, partials_ld=self.width,
+                     gamma=a.p(f"MLPs.{v}.batchnorm.weight"), beta=a.p(f"MLPs.{v}.batchnorm.bias"),
+                     momentum=MOMENTUM, eps=EPS, train=int(train), act=1, p_drop=0.1 if train else 0.0,
+                     mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
+                     seed=eng.seed + 7919 * (i + 1), seed_dev=eng.arena.step.data_ptr(),
+                     out=fptr(ws["Dh"], c0), ldo=ws["Dh"].stride(0), saved=ws["saved"][i].data_ptr(),
+                     **_bn_ptrs(mlp.batchnorm))
+            bias = a.p(f"MLPs.{v}.layer_out.bias") if mlp.layer_out.bias is not None else None
+            kind = self.kinds[v] if with_loss else 0
+            slot = self.loss_names.index(v)
+            yv = None
+            if with_loss and kind in (1, 2):
+                yv = y[v].data_ptr()
+            L.head_out_fwd(fptr(ws["Dh"], c0), ws["Dh"].stride(0), B, self.sh, a.p(f"MLPs.{v}.layer_out.weight"), bias,
+                           self.C[v], ws["logits"][v].data_ptr(), self.C[v], kind if kind in (1, 2) else 0, yv,
+                           fptr(ws["acc"], 2 * slot))
+            if with_loss and kind == 3:
+                L.cox_fwd(ws["logits"][v].data_ptr(), 1, y[self.surv_time].data_ptr(), y[self.surv_event].data_ptr(), B,
+                          ws["coef"].data_ptr(), fptr(ws["acc"], 2 * slot))
+
+    def total(self, ws):
+        L.total_loss(self.n_losses, ws["acc"].data_ptr(), self.kinds_dev.data_ptr(),
+                     None if self.lv_dev is None else self.lv_dev.data_ptr(),
+                     None if self.dlv_dev is None else self.dlv_dev.data_ptr(), self.weighting, ws["out"].data_ptr())
+
+    def weight_ptr(self, ws, name: str) -> int:
+        return fptr(ws["out"], self.n_losses + 2 + self.loss_names.index(name))
+
+    # ---- backward: fills head grads and writes dF (planes, optional fp32 accumulate target) ----
+    def backward(self, ws, Fp: Planes, B: int, y, masks, dF: Planes, dF_f32=None, dbias_ptr=None, accumulate=False):
+        eng, a = self.eng, self.eng.arena
+        if not self.vars:
+            return False
+        model = eng.model
+        for i, v in enumerate(self.vars):
+            mlp = model.MLPs[v]
+            c0 = i * self.shp
+            slot = self.loss_names.index(v)
+            kind = self.kinds[v]
+            has_b = mlp.layer_out.bias is not None
+            L.head_out_bwd(fptr(ws["Dh"], c0), ws["Dh"].stride(0), B, self.sh, a.p(f"MLPs.{v}.layer_out.weight"),
+                           self.C[v], ws["logits"][v].data_ptr(), self.C[v], kind,
+                           y[v].data_ptr() if kind in (1, 2) else None, fptr(ws["acc"], 2 * slot),
+                           ws["coef"].data_ptr() if kind == 3 else None, self.weight_ptr(ws, v),
+                           fptr(ws["dDh"], c0), ws["dDh"].stride(0), a.g(f"MLPs.{v}.layer_out.weight"),
+                           a.g(f"MLPs.{v}.layer_out.bias") if has_b else None)
+            mask = None if masks is None else masks.get(f"MLPs.{v}.dropout")
+            dz = ws["dZh"].cols_view(c0, self.sh)
+            L.bn_bwd(V=fptr(ws["Zh"], c0), ldv=ws["Zh"].stride(0), dOut=fptr(ws["dDh"], c0), ldg=ws["dDh"].stride(0),
+                     rows=B, cols=self.sh, gamma=a.p(f"MLPs.{v}.batchnorm.weight"), beta=a.p(f"MLPs.{v}.batchnorm.bias"),
+                     saved=ws["saved"][i].data_ptr(), act=1, p_drop=0.1,
+                     mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
+                     seed=eng.seed + 7919 * (i + 1), seed_dev=eng.arena.step.data_ptr(), pre_act=0,
+                     sums=ws["sums"][i].data_ptr(), dgamma=a.g(f"MLPs.{v}.batchnorm.weight"),
+                     dbeta=a.g(f"MLPs.{v}.batchnorm.bias"), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+            # dW1_v [sh x L] = dZh_v^T * F
+            L.gemm(self.sh, self.L, B, dz, 1, Fp, 1, C_ptr=a.g(f"MLPs.{v}.layer_1.weight"), ldc=self.L, splitk=-1)
+        # dF [B x L] = dZh_cat * W1cat   (+ column sums -> bias gradient of whatever produced F)
+        L.gemm(B, self.L, self.width, ws["dZh"], 0, self.w1_planes(), 1,
+               C_ptr=None if dF_f32 is None else dF_f32.data_ptr(), ldc=0 if dF_f32 is None else dF_f32.stride(0),
+               out=dF, colstats=dbias_ptr, stats_mode=3 if dbias_ptr is not None else 0, accumulate=accumulate)
+        return True
+
+
+# ----------------------------------------------------------------------------------------------------
+# DirectPred / MultiTripletNetwork
+# ----------------------------------------------------------------------------------------------------
+class TrunkEngine:
+    """Per-modality MLP encoders -> concat -> fusion Linear -> heads (DirectPred), run on G row-groups at once
+    (G = 3 for the triplet network: anchor / positive / negative share every GEMM but keep separate BatchNorm
+    statistics, as three separate forward calls do in the reference)."""
+
+    def __init__(self, model, device, groups: int = 1, extra_losses: Sequence[str] = ()):
+        self.model, self.device, self.G = model, torch.device(device), groups
+        self.seed = 0x5EED
+        self.arena = ParamArena(model, self.device)
+        self.wplanes = WeightPlanes(self.arena)
+        self.latent = int(model.config["latent_dim"])
+        self.n = len(model.encoders)
+        self.d = [e.layer_1.in_features for e in model.encoders]
+        self.h = [e.layer_1.out_features for e in model.encoders]
+        Lp = pad8(self.latent)
+        self.Lp = Lp
+        self.w1 = [self.wplanes.add_matrix(f"encoders.{i}.layer_1.weight") for i in range(self.n)]
+        self.w2 = [self.wplanes.add_matrix(f"encoders.{i}.layer_out.weight") for i in range(self.n)]
+        self.fused = model.fusion_block is not None
+        if self.fused:
+            self.wf_off = self.wplanes.reserve(self.latent, self.n * Lp)
+            for i in range(self.n):
+                self.wplanes.add_segment("fusion_block.weight", i * self.latent, self.latent, self.latent,
+                                         self.n * self.latent, self.wf_off + i * Lp, self.n * Lp)
+        self.heads = HeadsBlock(self, model, extra_losses)
+        self.wplanes.finalize()
+        self.wplanes.refresh()
+        self._versions = self.arena.versions()
+        self.inputs = InputCache()
+        self.ws: Dict[int, dict] = {}
+        self.graphs = {}
+
+    # -- helpers --
+    def ensure_fresh(self):
+        """Weight planes follow the fp32 parameters: refresh them if anything outside optimizer_step (a torch optimizer,
+        load_state_dict) changed the parameters since the last refresh."""
+        v = self.arena.versions()
+        if v != self._versions:
+            self.wplanes.refresh()
+            self._versions = v
+
+    def wp(self, t) -> Planes:
+        _, off, rows, cols, ld = t
+        return self.wplanes.planes(off, rows, cols, ld)
+
+    def wf_planes(self, i: Optional[int] = None) -> Planes:
+        full = self.wplanes.planes(self.wf_off, self.latent, self.n * self.Lp, self.n * self.Lp)
+        return full if i is None else full.cols_view(i * self.Lp, self.latent)
+
+    def workspace(self, B: int) -> dict:
+        if B in self.ws:
+            return self.ws[B]
+        dev, G = self.device, self.G
+        Bp = B if G == 1 else pad128(B)
+        R = G * Bp
+        ws = dict(B=B, Bp=Bp, R=R)
+        ws["X"] = [Planes.empty(R, self.d[i], dev) for i in range(self.n)]
+        ws["Z"] = [torch.zeros(R, pad8(self.h[i]), device=dev) for i in range(self.n)]
+        ws["D"] = [Planes.empty(R, self.h[i], dev) for i in range(self.n)]
+        ws["dD"] = [torch.zeros(R, pad8(self.h[i]), device=dev) for i in range(self.n)]
+        ws["dZ"] = [Planes.empty(R, self.h[i], dev) for i in range(self.n)]
+        mt = L.stat_tiles(Bp)
+        ws["partials"] = [torch.zeros(G, mt * 2 * self.h[i], device=dev) for i in range(self.n)]
+        ws["saved"] = [torch.zeros(G, 2 * self.h[i], device=dev) for i in range(self.n)]
+        ws["sums"] = [torch.zeros(G, 2 * self.h[i], device=dev) for i in range(self.n)]
+        ws["Ecat"] = torch.zeros(R, self.n * self.Lp, device=dev)
+        ws["Ecat_p"] = Planes.empty(R, self.n * self.Lp, dev, ld=self.n * self.Lp)
+        ws["dEcat_p"] = Planes.empty(R, self.n * self.Lp, dev, ld=self.n * self.Lp)
+        if self.fused:
+            ws["F"] = torch.zeros(R, self.Lp, device=dev)
+            ws["F_p"] = Planes.empty(R, self.latent, dev, ld=self.Lp)
+            ws["dF_p"] = Planes.empty(R, self.latent, dev, ld=self.Lp)
+        else:
+            ws["F"], ws["F_p"], ws["dF_p"] = ws["Ecat"], ws["Ecat_p"], ws["dEcat_p"]
+        ws["dF"] = torch.zeros(R, self.Lp, device=dev)          # fp32 copy (triplet adds its own gradient here)
+        ws["rowloss"] = torch.zeros(B, device=dev)
+        ws["heads"] = self.heads.workspace(B)
+        self.ws[B] = ws
+        return ws
+
+    # -- input staging --
+    def stage_inputs(self, ws, groups: Sequence[Sequence[torch.Tensor]]):
+        for g, x_list in enumerate(groups):
+            for i, x in enumerate(x_list):
+                if x.device != self.device or x.dtype != torch.float32:
+                    x = x.to(self.device, torch.float32)
+                x = x.contiguous() if x.stride(-1) != 1 else x
+                dst = ws["X"][i].rows_view(g * ws["Bp"], ws["B"])
+                self.inputs.get((ws["B"], g, i), x, dst)
+
+    # -- forward of the trunk for all groups --
+    def trunk_forward(self, ws, train: bool, masks):
+        a, model = self.arena, self.model
+        B, Bp, R, G = ws["B"], ws["Bp"], ws["R"], self.G
+        mt = L.stat_tiles(Bp)
+        tags = [""] if G == 1 else ["anchor.", "positive.", "negative."]
+        for i in range(self.n):
+            enc = model.encoders[i]
+            h, hp = self.h[i], pad8(self.h[i])
+            use_epi_stats = train and G == 1
+            L.gemm(R, h, self.d[i], ws["X"][i], 0, self.wp(self.w1[i]), 0, C_ptr=ws["Z"][i].data_ptr(), ldc=hp,
+                   bias=a.p(f"encoders.{i}.layer_1.bias"),
+                   colstats=ws["partials"][i].data_ptr() if use_epi_stats else None, stats_mode=2)
+            for g in range(G):
+                r0 = g * Bp
+                if train and G > 1:
+                    L.col_stats(fptr(ws["Z"][i], r0 * hp), hp, B, h, 128, ws["partials"][i][g].data_ptr())
+                mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
+                D = ws["D"][i].rows_view(r0, B)
+                L.bn_fwd(V=fptr(ws["Z"][i], r0 * hp), ldv=hp, rows=B, cols=h,
+                         partials=ws["partials"][i][g].data_ptr(), ntiles=L.stat_tiles(B), tile_rows=128,
+                         gamma=a.p(f"encoders.{i}.batchnorm.weight"), beta=a.p(f"encoders.{i}.batchnorm.bias"),
+                         momentum=MOMENTUM, eps=EPS, train=int(train), act=1, p_drop=0.1 if train else 0.0,
+                         mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
+                         seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=a.step.data_ptr(),
+                         out_hi=D.hi_ptr, out_lo=D.lo_ptr, ldp=D.ld, saved=ws["saved"][i][g].data_ptr(),
+                         **_bn_ptrs(enc.batchnorm))
+            E_p = ws["Ecat_p"].cols_view(i * self.Lp, self.latent)
+            bias2 = a.p(f"encoders.{i}.layer_out.bias") if enc.layer_out.bias is not None else None
+            L.gemm(R, self.latent, h, ws["D"][i], 0, self.wp(self.w2[i]), 0, C_ptr=fptr(ws["Ecat"], i * self.Lp),
+                   ldc=self.n * self.Lp, bias=bias2, out=E_p)
+        if self.fused:
+            L.gemm(R, self.latent, self.n * self.Lp, ws["Ecat_p"], 0, self.wf_planes(), 0, C_ptr=ws["F"].data_ptr(),
+                   ldc=self.Lp, bias=a.p("fusion_block.bias"), out=ws["F_p"])
+
+    # -- backward of the trunk given dF planes (all groups) --
+    def trunk_backward(self, ws, masks):
+        a, model = self.arena, self.model
+        B, Bp, R, G = ws["B"], ws["Bp"], ws["R"], self.G
+        tags = [""] if G == 1 else ["anchor.", "positive.", "negative."]
+        Lt, Lp = self.latent, self.Lp
+        for i in range(self.n):
+            enc = model.encoders[i]
+            h, hp = self.h[i], pad8(self.h[i])
+            dE = ws["dEcat_p"].cols_view(i * Lp, Lt)
+            E_p = ws["Ecat_p"].cols_view(i * Lp, Lt)
+            has_b2 = enc.layer_out.bias is not None
+            if self.fused:
+                # dE_i = dF * Wf[:, iL:(i+1)L]   (+ column sums -> d layer_out.bias)
+                L.gemm(R, Lt, Lt, ws["dF_p"], 0, self.wf_planes(i), 1, out=dE,
+                       colstats=a.g(f"encoders.{i}.layer_out.bias") if has_b2 else None, stats_mode=3)
+                # dWf[:, iL:(i+1)L] = dF^T * E_i
+                L.gemm(Lt, Lt, R, ws["dF_p"], 1, E_p, 1, C_ptr=fptr(a.grad, a.offset["fusion_block.weight"] + i * Lt),
+                       ldc=self.n * Lt, splitk=-1)
+            # dD_i = dE_i * W2_i ; dW2_i = dE_i^T * D_i
+            L.gemm(R, h, Lt, dE, 0, self.wp(self.w2[i]), 1, C_ptr=ws["dD"][i].data_ptr(), ldc=hp)
+            L.gemm(Lt, h, R, dE, 1, ws["D"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_out.weight"), ldc=h, splitk=-1)
+            for g in range(G):
+                r0 = g * Bp
+                mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
+                dz = ws["dZ"][i].rows_view(r0, B)
+                first = g == 0
+                L.bn_bwd(V=fptr(ws["Z"][i], r0 * hp), ldv=hp, dOut=fptr(ws["dD"][i], r0 * hp), ldg=hp, rows=B, cols=h,
+                         gamma=a.p(f"encoders.{i}.batchnorm.weight"), beta=a.p(f"encoders.{i}.batchnorm.bias"),
+                         saved=ws["saved"][i][g].data_ptr(), act=1, p_drop=0.1,
+                         mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
+                         seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=a.step.data_ptr(), pre_act=0,
+                         sums=ws["sums"][i][g].data_ptr(),
+                         dgamma=a.g(f"encoders.{i}.batchnorm.weight"), dbeta=a.g(f"encoders.{i}.batchnorm.bias"),
+                         accumulate_affine=0 if first else 1,   # affine grads add up over the three triplet passes
+                         dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+            # dW1_i = dZ_i^T * X_i
+            L.gemm(h, self.d[i], R, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_1.weight"),
+                   ldc=self.d[i], splitk=-1)
+
+    # -- optimizer --
+    def optimizer_step(self, lr: float, max_norm: float = 1.0, grad_scale: float = 1.0):
+        a = self.arena
+        L.clip_adam(a.flat.data_ptr(), a.grad.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(), a.numel, lr,
+                    max_norm, grad_scale, a.sumsq.data_ptr(), a.step.data_ptr(), a.grad_norm.data_ptr())
+        self.wplanes.refresh()
+
+
+    # -- full steps --
+    def _labels(self, y: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        out = {}
+        for k, v in y.items():
+            if not torch.is_tensor(v):
+                continue
+            if v.device != self.device or v.dtype != torch.float32 or not v.is_contiguous():
+                v = v.to(self.device, torch.float32).contiguous()
+            out[k] = v
+        return out
+
+    def forward_backward(self, x_groups, y, masks=None):
+        """One training forward + backward. x_groups: G lists of per-layer [B x d] fp32 tensors. Fills arena.grad and
+        returns the heads workspace (loss values in ws['out'], logits in ws['logits'])."""
+        B = x_groups[0][0].shape[0]
+        ws = self.workspace(B)
+        hw = ws["heads"]
+        y = self._labels(y)
+        self.ensure_fresh()
+        self.stage_inputs(ws, x_groups)
+        hw["acc"].zero_()
+        self.trunk_forward(ws, True, masks)
+        Fa = ws["F_p"].rows_view(0, B)
+        self.heads.forward(hw, Fa, B, y, True, masks)
+        if self.G == 3:
+            Bp, Lp = ws["Bp"], self.Lp
+            L.triplet_fwd(ws["F"].data_ptr(), fptr(ws["F"], Bp * Lp), fptr(ws["F"], 2 * Bp * Lp), Lp, B, self.latent, 1.0,
+                          ws["rowloss"].data_ptr(), hw["acc"].data_ptr())
+        self.heads.total(hw)
+        # ---- backward ----
+        a = self.arena
+        if self.fused:
+            dbias = a.g("fusion_block.bias")
+        elif self.model.encoders[0].layer_out.bias is not None:
+            dbias = a.g("encoders.0.layer_out.bias")
+        else:
+            dbias = None
+        if self.G == 1:
+            self.heads.backward(hw, Fa, B, y, masks, ws["dF_p"].rows_view(0, B), None, dbias)
+        else:
+            Bp, Lp = ws["Bp"], self.Lp
+            self.heads.backward(hw, Fa, B, y, masks, ws["dF_p"].rows_view(0, B), ws["dF"], dbias)
+            L.triplet_bwd(ws["F"].data_ptr(), fptr(ws["F"], Bp * Lp), fptr(ws["F"], 2 * Bp * Lp), Lp, B, self.latent,
+                          ws["rowloss"].data_ptr(), self.heads.weight_ptr(hw, "triplet_loss"), ws["dF"].data_ptr(),
+                          fptr(ws["dF"], Bp * Lp), fptr(ws["dF"], 2 * Bp * Lp), Lp, True)
+            L.split_planes(ws["dF"][:, :self.latent], ws["dF_p"])
+        self.trunk_backward(ws, masks)
+        return ws
+
+    def evaluate(self, x_groups, y=None, train_mode: bool = False, masks=None):
+        """Forward only (eval-mode BatchNorm unless train_mode). Returns the workspace."""
+        B = x_groups[0][0].shape[0]
+        ws = self.workspace(B)
+        hw = ws["heads"]
+        self.ensure_fresh()
+        self.stage_inputs(ws, x_groups)
+        hw["acc"].zero_()
+        self.trunk_forward(ws, train_mode, masks)
+        yl = self._labels(y) if y is not None else None
+        self.heads.forward(hw, ws["F_p"].rows_view(0, B), B, yl, train_mode, masks, with_loss=y is not None)
+        if y is not None:
+            if self.G == 3:
+                Bp, Lp = ws["Bp"], self.Lp
+                L.triplet_fwd(ws["F"].data_ptr(), fptr(ws["F"], Bp * Lp), fptr(ws["F"], 2 * Bp * Lp), Lp, B, self.latent,
+                              1.0, ws["rowloss"].data_ptr(), hw["acc"].data_ptr())
+            self.heads.total(hw)
+        return ws
+
+    def embedding(self, ws, group: int = 0) -> torch.Tensor:
+        B, Bp = ws["B"], ws["Bp"]
+        return ws["F"][group * Bp:group * Bp + B, :self.latent]
+
+    def losses(self, ws) -> Dict[str, torch.Tensor]:
+        out = ws["heads"]["out"]
+        n = self.heads.n_losses
+        res = {name: out[i] for i, name in enumerate(self.heads.loss_names)}
+        res["__total__"], res["__val_total__"] = out[n], out[n + 1]
+        return res

@@ -1,0 +1,371 @@
+"""Drop-in model classes: same names, constructor signatures, attributes, methods and state_dict keys as
+flexynesis.models.{DirectPred, supervised_vae, MultiTripletNetwork, GNN}, with the training
+arithmetic executed by the B200 engine instead of torch autograd.
+
+What callers of the reference rely on and is kept:
+  * `Model(config, dataset, target_variables, batch_variables=None, surv_event_var=None, surv_time_var=None,
+    use_loss_weighting=True, device_type=None)`                                  direct_pred.py:30-40
+  * `training_step(batch, batch_idx, log=True)` / `validation_step(...)` return a scalar loss tensor on which
+    `.backward()` populates `.grad` of every parameter (Lightning then clips and steps)      :225-294
+  * `forward`, `configure_optimizers`, `compute_loss`, `compute_total_loss`, `predict`, `transform`, `forward_target`
+  * attributes `config, encoders, MLPs, log_vars, variables, target_variables, layers, input_dims, ...`
+New, optional: `fit_step(batch)` -- forward + backward + clip(1.0) + Adam fused on the device and CUDA-graph
+replayable; `fit(...)` in flexynesis_b200.fit drives it.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import Dict, List
+
+import numpy as np
+import pandas as pd
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .containers import MLP, Decoder, Encoder, flexGCN
+
+try:  # Lightning is optional: the reference trains under pl.Trainer, this engine also ships its own fit loop
+    import lightning as pl
+    _Base = pl.LightningModule
+except Exception:  # pragma: no cover - exercised on boxes without lightning
+    class _Base(nn.Module):
+        """Minimal stand-in for lightning.LightningModule (logging hooks + device property)."""
+
+        def __init__(self):
+            super().__init__()
+            self.logged = {}
+
+        def log(self, name, value, **kw):
+            self.logged[name] = value
+
+        def log_dict(self, d, **kw):
+            self.logged.update(d)
+
+        @property
+        def device(self):
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+
+def _resolve_device(device_type) -> torch.device:
+    s = (device_type or "auto")
+    s = s.lower() if isinstance(s, str) else "auto"
+    if s in ("gpu", "cuda", "auto") and torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    if s.startswith("cuda"):
+        return torch.device(s)
+    return torch.device("cpu")
+
+
+class _EngineLoss(torch.autograd.Function):
+    """Connects the engine's hand-written backward to autograd: the forward value is the engine's total loss, the
+    backward hands out the gradients the engine already computed (scaled by grad_output)."""
+
+    @staticmethod
+    def forward(ctx, total, holder, *params):
+        ctx.holder = holder
+        return total.detach().clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        arena = ctx.holder.arena
+        grads = [grad_out * arena.view(name, arena.grad) for name in arena.names]
+        return (None, None, *grads)
+
+
+class _EngineModel(_Base):
+    """Shared plumbing of the four models."""
+
+    engine_groups = 1
+    extra_losses = ()
+
+    # ---- engine lifetime (private cache: never pickled, never in state_dict) ----
+    def _make_engine(self, device):
+        raise NotImplementedError
+
+    def engine(self, device=None):
+        eng = self.__dict__.get("_engine")
+        if device is None:
+            device = next(self.parameters()).device
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("flexynesis_b200 trains on CUDA devices only (no CPU fallback); move the model with "
+                               ".to('cuda') or pass device_type='gpu'")
+        if eng is None or eng.device != device or not eng.arena.intact():
+            if next(self.parameters()).device != device:
+                self.to(device)
+            eng = self._make_engine(device)
+            self.__dict__["_engine"] = eng
+        return eng
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_engine", None)
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == "_engine":
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        # parameters of the copy must own their storage (the source's are views into its arena)
+        for p in new.parameters():
+            p.data = p.data.clone()
+        return new
+
+    # ---- reference API shared by all models ----
+    def configure_optimizers(self):
+        return torch.optim.Adam(self.parameters(), lr=self.config["lr"])
+
+    def compute_loss(self, var, y, y_hat):
+        """Torch formulation of the per-variable loss (API compatibility; the engine fuses this into its head
+        kernels). Missing labels (NaN, or -1 for categoricals) are excluded; no valid label -> 0."""
+        numeric = self.variable_types[var] == "numerical"
+        ok = ~torch.isnan(y) if numeric else ((y != -1) & ~torch.isnan(y))
+        if int(ok.sum()) == 0:
+            return torch.tensor(0.0, device=y_hat.device, requires_grad=True)
+        if numeric:
+            return F.mse_loss(torch.flatten(y_hat[ok]), y[ok].float())
+        return F.cross_entropy(y_hat[ok], y[ok].long())
+
+    def compute_total_loss(self, losses):
+        if self.use_loss_weighting and len(losses) > 1:
+            return sum(torch.exp(-self.log_vars[k]) * v + self.log_vars[k] for k, v in losses.items())
+        return sum(losses.values())
+
+    def _split_batch(self, batch):
+        dat, y_dict = batch[0], batch[1]
+        return [[dat[k] for k in dat.keys()]], y_dict
+
+    def _on_cuda(self, groups) -> bool:
+        return all(t.is_cuda for g in groups for t in g)
+
+    def training_step(self, train_batch, batch_idx, log=True, masks=None):
+        groups, y = self._split_batch(train_batch)
+        dev = groups[0][0].device if groups[0][0].is_cuda else next(self.parameters()).device
+        eng = self.engine(dev)
+        ws = eng.forward_backward(groups, y, masks)
+        vals = eng.losses(ws)
+        total = _EngineLoss.apply(vals["__total__"], eng, *[eng.arena.params[n] for n in eng.arena.names])
+        losses = {k: v.detach() for k, v in vals.items() if not k.startswith("__")}
+        losses["train_loss"] = total
+        if log:
+            self.log_dict(losses, on_step=False, on_epoch=True, prog_bar=True)
+        return total
+
+    def validation_step(self, val_batch, batch_idx, log=True):
+        groups, y = self._split_batch(val_batch)
+        dev = groups[0][0].device if groups[0][0].is_cuda else next(self.parameters()).device
+        eng = self.engine(dev)
+        ws = eng.evaluate(groups, y, train_mode=self.training)
+        vals = eng.losses(ws)
+        total = vals["__val_total__"].detach().clone()      # unweighted sum (direct_pred.py:290)
+        losses = {k: v.detach().clone() for k, v in vals.items() if not k.startswith("__")}
+        losses["val_loss"] = total
+        if log:
+            self.log_dict(losses, on_step=False, on_epoch=True, prog_bar=True)
+        return total
+
+    def fit_step(self, batch, lr=None, masks=None, grad_scale: float = 1.0, allreduce=None):
+        """forward + backward + clip_grad_norm_(1.0) + Adam, all on the engine. `allreduce(flat_grad)` (optional) is
+        called between backward and the update (data-parallel training)."""
+        groups, y = self._split_batch(batch)
+        eng = self.engine(groups[0][0].device if groups[0][0].is_cuda else None)
+        ws = eng.forward_backward(groups, y, masks)
+        if allreduce is not None:
+            allreduce(eng.arena.grad)
+        eng.optimizer_step(float(self.config["lr"] if lr is None else lr), 1.0, grad_scale)
+        return ws
+
+    # ---- inference helpers ----
+    def _batches(self, dataset, batch_size):
+        n = len(dataset)
+        keys = list(dataset.dat.keys())
+        for s in range(0, n, batch_size):
+            yield [dataset.dat[k][s:s + batch_size] for k in keys], list(dataset.samples[s:s + batch_size])
+
+    def _outputs_from_ws(self, eng, ws) -> Dict[str, torch.Tensor]:
+        return {v: ws["heads"]["logits"][v].clone() for v in eng.heads.vars}
+
+
+class DirectPred(_EngineModel):
+    """Fully connected multi-omics network with supervisor heads (flexynesis/models/direct_pred.py)."""
+
+    def __init__(self, config, dataset, target_variables, batch_variables=None, surv_event_var=None,
+                 surv_time_var=None, use_loss_weighting=True, device_type=None):
+        super().__init__()
+        self.config = config
+        self.target_variables = target_variables
+        self.surv_event_var, self.surv_time_var = surv_event_var, surv_time_var
+        if surv_event_var is not None and surv_time_var is not None:
+            self.target_variables = self.target_variables + [surv_event_var]
+        self.batch_variables = batch_variables
+        self.variables = self.target_variables + batch_variables if batch_variables else self.target_variables
+        self.feature_importances = {}
+        self.use_loss_weighting = use_loss_weighting
+        self.device_type = device_type
+        if use_loss_weighting:
+            self.log_vars = nn.ParameterDict({v: nn.Parameter(torch.zeros(1)) for v in self._loss_names()})
+        self.variable_types = dataset.variable_types
+        self.ann = dataset.ann
+        self.layers = list(dataset.dat.keys())
+        self.input_dims = [len(dataset.features[k]) for k in self.layers]
+        latent = config["latent_dim"]
+        self.encoders = nn.ModuleList(
+            [MLP(d, int(d * config["hidden_dim_factor"]), latent) for d in self.input_dims])
+        self.fusion_block = nn.Linear(latent * len(self.layers), latent) if len(self.layers) > 1 else None
+        self.MLPs = nn.ModuleDict()
+        for var in self.variables:
+            classes = 1 if self.variable_types[var] == "numerical" else len(np.unique(self.ann[var]))
+            self.MLPs[var] = MLP(latent, config["supervisor_hidden_dim"], classes)
+
+    def _loss_names(self) -> List[str]:
+        return list(self.variables)
+
+    def _make_engine(self, device):
+        from .engine import TrunkEngine
+        return TrunkEngine(self, device, groups=1)
+
+    def forward(self, x_list):
+        """{var: head output}. CUDA inputs without input-gradients run on the engine; anything else (captum's
+        requires_grad inputs, CPU-resident inference) uses the differentiable torch formulation of the containers."""
+        x_list = list(x_list)
+        use_engine = all(x.is_cuda and not x.requires_grad for x in x_list) and not (
+            self.training and torch.is_grad_enabled())
+        if use_engine:
+            eng = self.engine(x_list[0].device)
+            ws = eng.evaluate([x_list], None, train_mode=self.training)
+            return self._outputs_from_ws(eng, ws)
+        emb = self._embed_torch(x_list)
+        return {var: mlp(emb) for var, mlp in self.MLPs.items()}
+
+    def _embed_torch(self, x_list):
+        cat = torch.cat([enc(x) for enc, x in zip(self.encoders, x_list)], dim=1)
+        return self.fusion_block(cat) if self.fusion_block is not None else cat
+
+    def predict(self, dataset):
+        """{var: np.ndarray}: class probabilities for categorical variables, raw outputs otherwise (:296-351)."""
+        self.eval()
+        device = _resolve_device(self.device_type)
+        self.to(device)
+        preds = {v: [] for v in self.variables}
+        with torch.no_grad():
+            for xs, _ in self._batches(dataset, 4096 if device.type == "cuda" else 64):
+                out = self.forward([x.to(device, torch.float32) for x in xs])
+                for v in self.variables:
+                    o = out[v].detach().float().cpu()
+                    preds[v].append(torch.softmax(o, dim=1) if dataset.variable_types[v] == "categorical" else o)
+        return {v: torch.cat(p).numpy() for v, p in preds.items()}
+
+    def transform(self, dataset):
+        """Fused embeddings as a DataFrame with columns E0.. indexed by sample name (:353-415)."""
+        self.eval()
+        device = _resolve_device(self.device_type)
+        self.to(device)
+        embs, names = [], []
+        with torch.no_grad():
+            for xs, samples in self._batches(dataset, 4096 if device.type == "cuda" else 64):
+                xs = [x.to(device, torch.float32) for x in xs]
+                if device.type == "cuda":
+                    eng = self.engine(device)
+                    ws = eng.evaluate([xs], None)
+                    e = eng.embedding(ws).clone()
+                else:
+                    e = self._embed_torch(xs)
+                embs.append(e.cpu())
+                names.extend(samples)
+        e = torch.cat(embs, 0)
+        return pd.DataFrame(e.numpy(), index=names, columns=[f"E{i}" for i in range(e.shape[1])])
+
+    def forward_target(self, *args):
+        """captum adaptor (direct_pred.py:418-431): args = (*layer_tensors[steps, B, d], target_var, steps)."""
+        inputs, target_var, steps = list(args[:-2]), args[-2], args[-1]
+        outs = []
+        for i in range(steps):
+            outs.append(self.forward([x[i] for x in inputs])[target_var])
+        return torch.cat(outs, dim=0)
+
+
+class MultiTripletNetwork(DirectPred):
+    """DirectPred trunk applied to (anchor, positive, negative) + triplet margin loss + heads on the anchor
+    (flexynesis/models/triplet_encoder.py). The first target variable must be categorical (:69-75)."""
+
+    def __init__(self, config, dataset, target_variables, batch_variables=None, surv_event_var=None,
+                 surv_time_var=None, use_loss_weighting=True, device_type=None):
+        main_var = target_variables[0]
+        if dataset.variable_types[main_var] == "numerical":
+            raise ValueError("The first target variable", main_var, " must be a categorical variable")
+        super().__init__(config, dataset, target_variables, batch_variables, surv_event_var, surv_time_var,
+                         use_loss_weighting, device_type)
+        self.main_var = main_var
+
+    def _loss_names(self):
+        return list(self.variables) + ["triplet_loss"]      # ParameterDict order of the reference (:81-84)
+
+    def _make_engine(self, device):
+        from .engine import TrunkEngine
+        return TrunkEngine(self, device, groups=3, extra_losses=(("triplet_loss", 1),))
+
+    def _split_batch(self, batch):
+        anchor, pos, neg, y = batch[0], batch[1], batch[2], batch[3]
+        return [[d[k] for k in d.keys()] for d in (anchor, pos, neg)], y
+
+    def concat_embeddings(self, dat):
+        return self._embed_torch([dat[k] for k in dat.keys()])
+
+    def forward(self, anchor, positive, negative):
+        """(anchor_emb, positive_emb, negative_emb, {var: head output on the anchor})."""
+        groups = [[d[k] for k in d.keys()] for d in (anchor, positive, negative)]
+        use_engine = all(x.is_cuda and not x.requires_grad for g in groups for x in g) and not (
+            self.training and torch.is_grad_enabled())
+        if use_engine:
+            eng = self.engine(groups[0][0].device)
+            ws = eng.evaluate(groups, None, train_mode=self.training)
+            return (eng.embedding(ws, 0).clone(), eng.embedding(ws, 1).clone(), eng.embedding(ws, 2).clone(),
+                    self._outputs_from_ws(eng, ws))
+        ea, ep, en = (self._embed_torch(g) for g in groups)
+        return ea, ep, en, {var: mlp(ea) for var, mlp in self.MLPs.items()}
+
+    def triplet_loss(self, anchor, positive, negative, margin=1.0):
+        dp = (anchor - positive).pow(2).sum(1)
+        dn = (anchor - negative).pow(2).sum(1)
+        return torch.relu(dp - dn + margin).mean()
+
+    def _anchor_only(self, xs):
+        return [xs, xs, xs]
+
+    def predict(self, dataset):
+        self.eval()
+        device = _resolve_device(self.device_type)
+        self.to(device)
+        preds = {v: [] for v in self.variables}
+        with torch.no_grad():
+            for xs, _ in self._batches(dataset, 4096 if device.type == "cuda" else 64):
+                xs = [x.to(device, torch.float32) for x in xs]
+                d = dict(zip(self.layers, xs))
+                out = self.forward(d, d, d)[3]
+                for v in self.variables:
+                    o = out[v].detach().float().cpu()
+                    preds[v].append(torch.softmax(o, dim=1) if dataset.variable_types[v] == "categorical" else o)
+        return {v: torch.cat(p).numpy() for v, p in preds.items()}
+
+    def transform(self, dataset):
+        self.eval()
+        device = _resolve_device(self.device_type)
+        self.to(device)
+        embs, names = [], []
+        with torch.no_grad():
+            for xs, samples in self._batches(dataset, 4096 if device.type == "cuda" else 64):
+                xs = [x.to(device, torch.float32) for x in xs]
+                d = dict(zip(self.layers, xs))
+                embs.append(self.forward(d, d, d)[0].cpu())
+                names.extend(samples)
+        e = torch.cat(embs, 0)
+        return pd.DataFrame(e.numpy(), index=names, columns=[f"E{i}" for i in range(e.shape[1])])

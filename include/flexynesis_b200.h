@@ -37,9 +37,15 @@ long long fxn_launch_count(void);
 void fxn_reset_launch_count(void);
 
 /* ---- operand planes ---- */
-/* planes(hi,lo)[r, c] = split(src[r, c]); columns [cols, ld_planes) are zero-filled. */
+/* planes(hi,lo)[r, c] = split(src[r, c]); columns [cols, pad8(cols)) are zero-filled. */
 int fxn_split_planes(const float* src, long long ld_src, long long rows, long long cols, void* hi, void* lo,
                      long long ld_planes, void* stream);
+
+/* Batch feeder: row gather out[b,:] = src[idx[b],:] (idx int64 device array, NULL = identity) written as fp32
+ * and/or planes. Replaces per-sample MultiOmicDataset.__getitem__ + default_collate (flexynesis/data.py:980-995)
+ * for a dataset resident in HBM. */
+int fxn_gather_rows(const float* src, long long ld_src, const long long* idx, long long nrows, long long cols,
+                    float* out, long long ldo, void* hi, void* lo, long long ldp, void* stream);
 
 /* ---- dense contraction on tcgen05 tensor cores ----
  * C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]).
@@ -57,12 +63,113 @@ typedef struct fxn_gemm_desc {
   const float* bias;       /* [N] or NULL */
   void* c_hi; void* c_lo; long long ldp; /* optional planes of the result */
   float* colstats;         /* optional [fxn_gemm_stat_tiles(M)][2][N]: per 128-row tile (sum, M2 about tile mean) */
-  int stats_mode;          /* 0/2: sum + M2, 1: sum only (M2 slot written as 0) */
-  int splitk;              /* >1: split K over blockIdx.z, fp32 atomics into C (C is zeroed by the call) */
+  int stats_mode;          /* 0/2: sum + M2; 1: sum only; 3: colstats is an [N] vector (zeroed by the call) receiving
+                              plain column sums by atomics (bias gradients) */
+  int splitk;              /* >1: split K over blockIdx.z, fp32 atomics into C (C is zeroed by the call); <0: auto */
   int block_n;             /* 0 = auto */
+  int epi_act;             /* applied after alpha and bias: 0 none, 1 relu, 3 sigmoid, 6 leaky_relu(0.2) */
+  int accumulate;          /* C += result instead of C = result */
+  float alpha;             /* result scale (0 means 1) ... */
+  const float* alpha_dev;  /* ... times *alpha_dev when not NULL (device scalar, e.g. a loss weight) */
+  /* fused Decoder output + reconstruction loss (flexynesis/modules.py:101-102 + supervised_vae.py:549):
+   * with epi_act = 3 the staged tile is x_hat = sigmoid(.); if mse_x != NULL the epilogue adds sum (x_hat - x)^2
+   * to *mse_acc and the planes (c_hi, c_lo) receive G = (x_hat - x) * x_hat * (1 - x_hat) -- the gradient of the
+   * squared error w.r.t. the pre-sigmoid output up to the constant 2/(M*N). C (if given) still receives x_hat. */
+  const float* mse_x; long long ldx; float* mse_acc;
 } fxn_gemm_desc;
 int fxn_gemm(const fxn_gemm_desc* d, void* stream);
 int fxn_gemm_stat_tiles(int M);
+
+/* ---- BatchNorm1d (+ activation + dropout) ----
+ * Forward of  y = dropout(act(BN(V)))  over the rows of V [rows x cols].
+ * Replaces aten::native_batch_norm + relu + dropout of MLP.forward (flexynesis/modules.py:146-148), the
+ * BatchNorm1d of Encoder/Decoder.hidden_layers (modules.py:28, :78; their LeakyReLU runs in the producing
+ * fxn_gemm via epi_act = 6) and flexGCN's bn -> act -> dropout (modules.py:255-257).
+ * train != 0: batch statistics from `partials` ([ntiles][2][cols], tile_rows rows per tile, written by
+ *   fxn_gemm(colstats) or fxn_col_stats), running stats updated with `momentum` (unbiased variance),
+ *   *num_batches_tracked += 1, (mean, rstd) stored in `saved` [2][cols] for the backward pass.
+ *   rows < 2 is an error, as in torch ("Expected more than 1 value per channel when training").
+ * train == 0: running statistics, no dropout.
+ * act: 0 none, 1 relu, 2 leaky_relu(0.01), 3 sigmoid, 4 tanh, 5 gelu.
+ * Dropout keep-mask: `mask` (uint8 [rows x cols], ld = ldm) when given, else Philox(seed, element index).
+ */
+typedef struct fxn_bn_fwd_desc {
+  const float* V; long long ldv; long long rows; int cols;
+  const float* partials; int ntiles; int tile_rows;
+  int partials_ld;                           /* columns of the partials array (0 = cols); lets V be a column window */
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; void* num_batches_tracked; /* int64 */
+  float momentum; float eps;
+  int train; int act; float p_drop;
+  const uint8_t* mask; long long ldm; unsigned long long seed;
+  const void* seed_dev;                      /* optional device int64 mixed into the seed (per-step counter) */
+  float* out; long long ldo;                 /* optional fp32 output */
+  void* out_hi; void* out_lo; long long ldp; /* optional planes of the output */
+  float* saved;
+} fxn_bn_fwd_desc;
+int fxn_bn_act_fwd(const fxn_bn_fwd_desc* d, void* stream);
+
+/* Backward of the same block: given dOut (gradient w.r.t. dropout(act(BN(V)))) produce dgamma, dbeta and dV
+ * (fp32 and/or planes). pre_act != 0: V is leaky_relu_0.2(Z) of the Linear output Z (Encoder/Decoder order); the
+ * result is multiplied by the LeakyReLU derivative so it is dZ, and dbias [cols] receives its column sum.
+ * `sums` is scratch [2][cols]. Autograd dual of the forward ops listed above. */
+typedef struct fxn_bn_bwd_desc {
+  const float* V; long long ldv; const float* dOut; long long ldg; long long rows; int cols;
+  const float* gamma; const float* beta; const float* saved;
+  int act; float p_drop; const uint8_t* mask; long long ldm; unsigned long long seed;
+  const void* seed_dev;
+  int pre_act;
+  float* sums; float* dgamma; float* dbeta; float* dbias;
+  float* dV; long long ldd;
+  void* dv_hi; void* dv_lo; long long ldp;
+  float grad_scale;      /* multiplies dOut; 0 means 1 */
+  int accumulate_affine; /* dgamma/dbeta += instead of = (a module applied several times per step) */
+} fxn_bn_bwd_desc;
+int fxn_bn_act_bwd(const fxn_bn_bwd_desc* d, void* stream);
+
+/* Column statistics partials of V for inputs that do not come from an fxn_gemm epilogue. */
+int fxn_col_stats(const float* V, long long ldv, long long rows, int cols, int tile_rows, float* partials, void* stream);
+
+/* ---- supervisor heads and losses ----
+ * logits[rows x C] = D[rows x sh] * W[C x sh]^T (+ bias). kind: 0 none (Cox risk score), 1 MSE over rows with
+ * non-NaN y, 2 cross-entropy over rows with y != -1 and non-NaN. acc[0] += sum of row losses, acc[1] += valid rows
+ * (caller zeroes acc). Replaces MLP.layer_out (modules.py:149) + compute_loss (direct_pred.py:146-190). */
+int fxn_head_out_fwd(const float* D, long long ldd, int rows, int sh, const float* W, const float* bias, int C,
+                     float* logits, long long ldl, int kind, const float* y, float* acc, void* stream);
+/* Backward: dlogits from (kind, y, acc[1], *weight) or from Cox coefficients (kind 3), then dD[rows x sh] (stored),
+ * dW[C x sh] and dbias[C] (zeroed by the call, accumulated). */
+int fxn_head_out_bwd(const float* D, long long ldd, int rows, int sh, const float* W, int C, const float* logits,
+                     long long ldl, int kind, const float* y, const float* acc, const float* coef,
+                     const float* weight, float* dD, long long ldg, float* dW, float* dbias, void* stream);
+/* Cox partial-likelihood loss of risk scores o[n] (stride ldo) -- cox_ph_loss, modules.py:265-305: rows with NaN
+ * duration/event dropped, sorted by duration descending, loss = -(sum_{e=1} o_i - log cumsum exp(o))/sum e, 0 when
+ * empty or non-finite. acc[0] = loss, acc[1] = 1; coef[n] = d loss / d o. */
+int fxn_cox_fwd(const float* o, long long ldo, const float* durations, const float* events, int n, float* coef,
+                float* acc, void* stream);
+int fxn_cox_max_rows(void);
+/* compute_total_loss (direct_pred.py:192-223). acc [n][2]; kinds[n] (device): 1 = mean of (sum, count), 3 = value in
+ * acc[k][0]. out: [0,n) losses, [n] total, [n+1] unweighted sum (validation objective, :290), [n+2, 2n+2) weights
+ * d total / d loss_k. With weighting and n > 1, *dlog_vars[k] = 1 - exp(-s_k) * loss_k. Pointer tables are device arrays. */
+int fxn_total_loss(int n, const float* acc, const int* kinds, const float* const* log_vars, float* const* dlog_vars,
+                   int weighting, float* out, void* stream);
+/* triplet_loss (triplet_encoder.py:178-194): mean_b relu(|a-p|^2 - |a-n|^2 + margin); acc as above. */
+int fxn_triplet_fwd(const float* A, const float* P, const float* N, long long ld, int rows, int L, float margin,
+                    float* rowloss, float* acc, void* stream);
+int fxn_triplet_bwd(const float* A, const float* P, const float* N, long long ld, int rows, int L,
+                    const float* rowloss, const float* weight, float* dA, float* dP, float* dN, long long ldg,
+                    int accumulate_a, void* stream);
+
+/* ---- step policy ----
+ * clip_grad_norm_(params, max_norm) + Adam on flat arenas (flexynesis/main.py:216-217, direct_pred.py:135-144).
+ * grads are multiplied by grad_scale (1/world_size after a sum all-reduce) before the norm. *step_counter (int64)
+ * is incremented by the call; norm_out (optional) receives the pre-clip norm. */
+int fxn_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                       float beta1, float beta2, float eps, float max_norm, float grad_scale, double* sumsq_scratch,
+                       long long* step_counter, float* norm_out, void* stream);
+/* Refresh the operand planes of many weight matrices in one launch. segments_dev: device array of nseg records
+ * {int64 src_off, rows, cols, ld_src, dst_off, ldp} (element offsets into src / the plane arenas). */
+int fxn_split_planes_multi(const float* src, const void* segments_dev, int nseg, long long max_seg_elems, void* hi,
+                           void* lo, void* stream);
 
 #ifdef __cplusplus
 }

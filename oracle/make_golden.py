@@ -120,6 +120,7 @@ def run_reference(name: str, sc) -> dict:
     opt = model.configure_optimizers()
     steps = []
     for s in range(STEPS):
+        P_before = copy.deepcopy(model.state_dict())
         with ref_shim.NoiseRecorder(model, triplet=(spec.model == "MultiTripletNetwork")) as rec:
             torch.manual_seed(100 + s)
             opt.zero_grad(set_to_none=True)
@@ -147,7 +148,7 @@ def run_reference(name: str, sc) -> dict:
             grads = {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in model.named_parameters()}
             gnorm = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
             opt.step()
-        steps.append(dict(noise={k: v.detach().clone() for k, v in rec.record.items()},
+        steps.append(dict(P_before=P_before, noise={k: v.detach().clone() for k, v in rec.record.items()},
                           outputs={k: v.detach().clone() for k, v in captured["outputs"].items()},
                           embedding=None if "emb" not in captured else captured["emb"].detach().clone(),
                           losses=logged, total=loss.detach().clone(), grads=grads, grad_norm=gnorm.detach().clone()))
