@@ -210,6 +210,10 @@ def run_b200(args, w):
     launches = step.launches_per_step * args.steps
     final_loss = float(step.losses()["__total__"])
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "launches_per_step": step.launches_per_step}))
+        return
     # ---------------- end-to-end arm (host batch -> device every step, loss read back every step) ----------------
     host = {k: v.pin_memory() for k, v in ds.dat.items()}
     host_y = {k: v.pin_memory() for k, v in ds.ann.items()}
@@ -320,6 +324,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile", action="store_true", help="timed steps only (for ncu launch lists): no e2e/roofline/cpu legs")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -87,7 +87,7 @@ struct BnArgs {
 };
 
 constexpr int BN_COLS = 64;     // columns per block (8 per thread x 8 threads)
-constexpr int BN_ROWS = 256;    // rows per block
+constexpr int BN_ROWS = 64;     // rows per block (2 per thread): many small blocks keep HBM requests in flight
 constexpr int BN_THREADS = 256;
 
 // merge tile partials for one column -> (mean, biased var)
@@ -109,32 +109,61 @@ __device__ __forceinline__ void merge_stats(const float* partials, int ntiles, i
 
 __global__ void __launch_bounds__(BN_THREADS) bn_fwd_kernel(const BnArgs a) {
   __shared__ float s_scale[BN_COLS], s_shift[BN_COLS];
+  __shared__ float s_red[4][BN_COLS];
+  __shared__ float s_mean[BN_COLS];
   const int c0 = blockIdx.x * BN_COLS;
-  if (threadIdx.x < BN_COLS) {
-    const int c = c0 + threadIdx.x;
-    float sc = 0.f, sh = 0.f;
-    if (c < a.cols) {
-      float mean, var;
-      if (a.train) {
-        merge_stats(a.partials, a.ntiles, a.tile_rows, a.rows, a.pld, c, mean, var);
-      } else {
-        mean = a.running_mean[c];
-        var = a.running_var[c];
-      }
-      const float rstd = rsqrtf(var + a.eps);
-      sc = a.gamma[c] * rstd;
-      sh = a.beta[c] - mean * sc;
-      if (a.train && blockIdx.y == 0) {
-        if (a.saved) { a.saved[c] = mean; a.saved[a.cols + c] = rstd; }
-        if (a.running_mean) {
-          const float n = static_cast<float>(a.rows);
-          a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * mean;
-          a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * var * n / (n - 1.f);
+  {
+    // batch statistics: 4 threads per column stride over the tile partials (Chan merge in two passes)
+    const int col = threadIdx.x & (BN_COLS - 1), lane4 = threadIdx.x >> 6;
+    const int c = c0 + col;
+    const bool ok = c < a.cols;
+    if (a.train) {
+      float part = 0.f;
+      if (ok)
+        for (int t = lane4; t < a.ntiles; t += 4) part += a.partials[(static_cast<long long>(t) * 2) * a.pld + c];
+      s_red[lane4][col] = part;
+      __syncthreads();
+      if (lane4 == 0) s_mean[col] = (s_red[0][col] + s_red[1][col] + s_red[2][col] + s_red[3][col]) / static_cast<float>(a.rows);
+      __syncthreads();
+      const float mean = s_mean[col];
+      float m2 = 0.f;
+      if (ok)
+        for (int t = lane4; t < a.ntiles; t += 4) {
+          const long long r0 = static_cast<long long>(t) * a.tile_rows;
+          const float n = static_cast<float>(min(static_cast<long long>(a.tile_rows), a.rows - r0));
+          const float d = a.partials[(static_cast<long long>(t) * 2) * a.pld + c] / n - mean;
+          m2 += a.partials[(static_cast<long long>(t) * 2 + 1) * a.pld + c] + n * d * d;
+        }
+      __syncthreads();
+      s_red[lane4][col] = m2;
+      __syncthreads();
+    }
+    if (lane4 == 0) {
+      float sc = 0.f, sh = 0.f;
+      if (ok) {
+        float mean, var;
+        if (a.train) {
+          mean = s_mean[col];
+          var = (s_red[0][col] + s_red[1][col] + s_red[2][col] + s_red[3][col]) / static_cast<float>(a.rows);
+        } else {
+          mean = a.running_mean[c];
+          var = a.running_var[c];
+        }
+        const float rstd = rsqrtf(var + a.eps);
+        sc = a.gamma[c] * rstd;
+        sh = a.beta[c] - mean * sc;
+        if (a.train && blockIdx.y == 0) {
+          if (a.saved) { a.saved[c] = mean; a.saved[a.cols + c] = rstd; }
+          if (a.running_mean) {
+            const float n = static_cast<float>(a.rows);
+            a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * mean;
+            a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * var * n / (n - 1.f);
+          }
         }
       }
+      s_scale[col] = sc;
+      s_shift[col] = sh;
     }
-    s_scale[threadIdx.x] = sc;
-    s_shift[threadIdx.x] = sh;
   }
   if (a.train && a.num_batches && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.num_batches += 1;
   __syncthreads();

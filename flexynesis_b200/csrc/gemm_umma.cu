@@ -359,15 +359,50 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, long long 
   return 0;
 }
 
-static int pick_bn(int N, int b_mn) {
-  int bn;
-  if (N >= 256) bn = 256;
-  else if (N > 128) bn = ((N + 63) / 64) * 64;
-  else bn = ((N + 15) / 16) * 16;
-  if (bn < 16) bn = 16;
-  if (b_mn) bn = ((bn + 63) / 64) * 64;  // MN-major B is loaded in 64-wide atoms
-  if (bn > 256) bn = 256;
-  return bn;
+// Tile width / split-K selection by a small analytic cost model (times in microseconds, B200 constants).
+// A CTA's k-block costs max(MMA issue time, operand load time); the chip moves at most ~L2_BW bytes/us from L2 to
+// the SMs, a single SM at most SM_BW; a launch costs its waves times the CTA time.
+struct TileChoice { int bn; int splitk; };
+
+static TileChoice choose_tile(int M, int N, int K, int nterms, int b_mn, bool allow_split) {
+  const double SM_CLK = 1.85e3;           // cycles per us under load
+  const double L2_BW = 9.0e6;             // bytes per us, whole chip (~9 TB/s L2 -> SM)
+  const double SM_BW = 1.6e5;             // bytes per us, one SM
+  const int nplanes = nterms == 3 ? 2 : 1;
+  const int kb_total = (K + BK - 1) / BK;
+  const int mt = (M + BM - 1) / BM;
+  const int step = b_mn ? 64 : 16;
+  TileChoice best{256, 1};
+  double best_t = 1e30;
+  for (int bn = step; bn <= 256; bn += step) {
+    const int nt = (N + bn - 1) / bn;
+    if (nt > 1 && bn < 64) continue;                       // narrow tiles only when one tile covers N
+    if (nt > 1 && (nt - 1) * bn >= N) continue;
+    const int stage_bytes = nplanes * (BM * BK * 2 + bn * BK * 2);
+    int stages = (231424 - 1024) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 1) continue;
+    for (int sk = 1; sk <= 32; sk *= 2) {
+      if (sk > 1 && (!allow_split || kb_total / sk < 2)) break;
+      const int ctas = mt * nt * sk;
+      const int kb = (kb_total + sk - 1) / sk;
+      const int active = ctas < 148 ? ctas : 148;
+      const double t_mma = nterms * 4.0 * (bn / 2.0) / SM_CLK;                 // 4 K-steps x nterms MMAs of 128 x bn x 16
+      double bw = L2_BW / active;
+      if (bw > SM_BW) bw = SM_BW;
+      const double t_load = stage_bytes / bw;
+      // with few stages the first loads are exposed; deep pipelines hide everything but the slower of the two rates
+      const double lat = 1.6;                                                 // TMA round trip
+      double t_loop = kb * (t_mma > t_load ? t_mma : t_load);
+      const double exposed = lat * (stages >= kb ? 1.0 : (stages >= 3 ? 1.0 : 1.0 + 0.5 * kb / stages));
+      const double t_epi = 1.0 + 3.0 * bn / 256.0 + (sk > 1 ? 1.5 * bn / 256.0 : 0.0);
+      const double t_cta = 2.0 + exposed + t_loop + t_epi;
+      const int waves = (ctas + 147) / 148;
+      double t = waves * t_cta + (sk > 1 ? 2.0 : 0.0);                        // split-K also pays a memset
+      if (t < best_t) { best_t = t; best = TileChoice{bn, sk}; }
+    }
+  }
+  return best;
 }
 
 }  // namespace fxn
@@ -388,7 +423,9 @@ extern "C" int fxn_gemm(const fxn_gemm_desc* d, void* stream_) {
   p.a_mn = d->a_mn_major ? 1 : 0;
   p.b_mn = d->b_mn_major ? 1 : 0;
   p.nterms = d->nterms;
-  p.bn = d->block_n > 0 ? d->block_n : pick_bn(d->N, p.b_mn);
+  const bool split_ok = d->splitk < 0 && d->C && !d->c_hi && !d->colstats && !d->epi_act && !d->accumulate && !d->mse_x;
+  const TileChoice tc_auto = choose_tile(d->M, d->N, d->K, d->nterms, p.b_mn, split_ok);
+  p.bn = d->block_n > 0 ? d->block_n : tc_auto.bn;
   if (p.bn % 16 != 0 || p.bn > 256 || (p.b_mn && p.bn % 64 != 0))
     return set_error(FXN_ERR_ARG, "fxn_gemm: invalid block_n %d", p.bn);
   const int nplanes = d->nterms == 3 ? 2 : 1;
@@ -399,15 +436,7 @@ extern "C" int fxn_gemm(const fxn_gemm_desc* d, void* stream_) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int kb_total = (d->K + BK - 1) / BK;
   int splitk = d->splitk > 1 ? d->splitk : 1;
-  if (d->splitk < 0) {   // auto: fill the 148 SMs when the output has few tiles and K is long (weight gradients)
-    const int tiles = ((d->M + BM - 1) / BM) * ((d->N + p.bn - 1) / p.bn);
-    splitk = 1;
-    if (tiles < 74 && kb_total >= 8) {
-      splitk = 148 / tiles;
-      if (splitk > kb_total / 4) splitk = kb_total / 4;
-      if (splitk < 1) splitk = 1;
-    }
-  }
+  if (d->splitk < 0) splitk = (d->block_n > 0) ? 1 : tc_auto.splitk;   // auto
   if (splitk > kb_total) splitk = kb_total;
   int kb_per = (kb_total + splitk - 1) / splitk;
   splitk = (kb_total + kb_per - 1) / kb_per;      // no empty splits

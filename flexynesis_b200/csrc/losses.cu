@@ -410,8 +410,8 @@ extern "C" int fxn_head_out_bwd(const float* D, long long ldd, int rows, int sh,
   cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * C * sh, stream);
   if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, sizeof(float) * C, stream);
   if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "head_out_bwd memset: %s", cudaGetErrorString(e));
-  int blocks = ceil_div(rows, HEAD_WARPS * 16);
-  if (blocks > 148) blocks = 148;
+  int blocks = ceil_div(rows, HEAD_WARPS * 2);
+  if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
   head_out_bwd_kernel<<<blocks, HEAD_WARPS * 32, smem, stream>>>(D, ldd, rows, sh, W, C, logits, ldl, kind, y, acc, coef,
                                                                 weight, dD, ldg, dW, dbias);

@@ -52,15 +52,28 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   const float step_size = lr / bc1;
   const float bc2_sqrt = sqrtf(bc2);
   if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = total_norm;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+  // arenas are 16B aligned and n % 8 == 0 (every parameter slot is padded to 8 floats): float4 all the way
+  const long long n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float gi = g[i] * coef;
-    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);          // lerp_
-    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;       // mul_ + addcmul_
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+    float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gi = ga[j] * coef;
+      const float mi = ma[j] + (gi - ma[j]) * omb1;           // lerp_
+      const float vi = va[j] * beta2 + omb2 * gi * gi;         // mul_ + addcmul_
+      ma[j] = mi;
+      va[j] = vi;
+      const float denom = sqrtf(vi) / bc2_sqrt + eps;
+      pa[j] = pa[j] - step_size * (mi / denom);
+    }
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
   }
 }
 
@@ -97,10 +110,12 @@ extern "C" int fxn_clip_adam_step(float* params, const float* grads, float* exp_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!params || !grads || !exp_avg || !exp_avg_sq || !sumsq_scratch || !step_counter || n <= 0)
     return set_error(FXN_ERR_ARG, "fxn_clip_adam_step: bad argument");
-  if (reinterpret_cast<uintptr_t>(grads) & 15) return set_error(FXN_ERR_ARG, "fxn_clip_adam_step: grads must be 16B aligned");
+  if ((reinterpret_cast<uintptr_t>(grads) & 15) || (reinterpret_cast<uintptr_t>(params) & 15) ||
+      (reinterpret_cast<uintptr_t>(exp_avg) & 15) || (reinterpret_cast<uintptr_t>(exp_avg_sq) & 15) || (n % 4) != 0)
+    return set_error(FXN_ERR_ARG, "fxn_clip_adam_step: arenas must be 16B aligned with n %% 4 == 0");
   cudaError_t e = cudaMemsetAsync(sumsq_scratch, 0, sizeof(double), stream);
   if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "clip_adam memset: %s", cudaGetErrorString(e));
-  int blocks = ceil_div(n, 256 * 8);
+  int blocks = ceil_div(n, 256 * 4 * 2);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   const float gs = grad_scale == 0.f ? 1.f : grad_scale;

@@ -331,9 +331,33 @@ class TrunkEngine:
         self._versions = self.arena.versions()
         self.inputs = InputCache()
         self.ws: Dict[int, dict] = {}
-        self.graphs = {}
+        # the per-modality encoder chains are independent until the fusion GEMM: run them on parallel streams (they
+        # become parallel branches of the captured CUDA graph) so that small tiles of one modality fill the SMs the
+        # other leaves idle
+        self.side = [torch.cuda.Stream(device=self.device) for _ in range(max(self.n - 1, 0))]
+        self.parallel_encoders = True
 
     # -- helpers --
+    def _stream_for(self, i: int):
+        if i == 0 or not self.parallel_encoders:
+            return torch.cuda.current_stream()
+        return self.side[i - 1]
+
+    def _fork(self):
+        if self.parallel_encoders and self.side:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            for st in self.side:
+                st.wait_event(ev)
+
+    def _join(self):
+        if self.parallel_encoders and self.side:
+            main = torch.cuda.current_stream()
+            for st in self.side:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                main.wait_event(ev)
+
     def ensure_fresh(self):
         """Weight planes follow the fp32 parameters: refresh them if anything outside optimizer_step (a torch optimizer,
         load_state_dict) changed the parameters since the last refresh."""
@@ -397,31 +421,34 @@ class TrunkEngine:
         B, Bp, R, G = ws["B"], ws["Bp"], ws["R"], self.G
         mt = L.stat_tiles(Bp)
         tags = [""] if G == 1 else ["anchor.", "positive.", "negative."]
+        self._fork()
         for i in range(self.n):
-            enc = model.encoders[i]
-            h, hp = self.h[i], pad8(self.h[i])
-            use_epi_stats = train and G == 1
-            L.gemm(R, h, self.d[i], ws["X"][i], 0, self.wp(self.w1[i]), 0, C_ptr=ws["Z"][i].data_ptr(), ldc=hp,
-                   bias=a.p(f"encoders.{i}.layer_1.bias"),
-                   colstats=ws["partials"][i].data_ptr() if use_epi_stats else None, stats_mode=2)
-            for g in range(G):
-                r0 = g * Bp
-                if train and G > 1:
-                    L.col_stats(fptr(ws["Z"][i], r0 * hp), hp, B, h, 128, ws["partials"][i][g].data_ptr())
-                mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
-                D = ws["D"][i].rows_view(r0, B)
-                L.bn_fwd(V=fptr(ws["Z"][i], r0 * hp), ldv=hp, rows=B, cols=h,
-                         partials=ws["partials"][i][g].data_ptr(), ntiles=L.stat_tiles(B), tile_rows=128,
-                         gamma=a.p(f"encoders.{i}.batchnorm.weight"), beta=a.p(f"encoders.{i}.batchnorm.bias"),
-                         momentum=MOMENTUM, eps=EPS, train=int(train), act=1, p_drop=0.1 if train else 0.0,
-                         mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
-                         seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=a.step.data_ptr(),
-                         out_hi=D.hi_ptr, out_lo=D.lo_ptr, ldp=D.ld, saved=ws["saved"][i][g].data_ptr(),
-                         **_bn_ptrs(enc.batchnorm))
-            E_p = ws["Ecat_p"].cols_view(i * self.Lp, self.latent)
-            bias2 = a.p(f"encoders.{i}.layer_out.bias") if enc.layer_out.bias is not None else None
-            L.gemm(R, self.latent, h, ws["D"][i], 0, self.wp(self.w2[i]), 0, C_ptr=fptr(ws["Ecat"], i * self.Lp),
-                   ldc=self.n * self.Lp, bias=bias2, out=E_p)
+          with torch.cuda.stream(self._stream_for(i)):
+              enc = model.encoders[i]
+              h, hp = self.h[i], pad8(self.h[i])
+              use_epi_stats = train and G == 1
+              L.gemm(R, h, self.d[i], ws["X"][i], 0, self.wp(self.w1[i]), 0, C_ptr=ws["Z"][i].data_ptr(), ldc=hp,
+                     bias=a.p(f"encoders.{i}.layer_1.bias"),
+                     colstats=ws["partials"][i].data_ptr() if use_epi_stats else None, stats_mode=2)
+              for g in range(G):
+                  r0 = g * Bp
+                  if train and G > 1:
+                      L.col_stats(fptr(ws["Z"][i], r0 * hp), hp, B, h, 128, ws["partials"][i][g].data_ptr())
+                  mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
+                  D = ws["D"][i].rows_view(r0, B)
+                  L.bn_fwd(V=fptr(ws["Z"][i], r0 * hp), ldv=hp, rows=B, cols=h,
+                           partials=ws["partials"][i][g].data_ptr(), ntiles=L.stat_tiles(B), tile_rows=128,
+                           gamma=a.p(f"encoders.{i}.batchnorm.weight"), beta=a.p(f"encoders.{i}.batchnorm.bias"),
+                           momentum=MOMENTUM, eps=EPS, train=int(train), act=1, p_drop=0.1 if train else 0.0,
+                           mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
+                           seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=a.step.data_ptr(),
+                           out_hi=D.hi_ptr, out_lo=D.lo_ptr, ldp=D.ld, saved=ws["saved"][i][g].data_ptr(),
+                           **_bn_ptrs(enc.batchnorm))
+              E_p = ws["Ecat_p"].cols_view(i * self.Lp, self.latent)
+              bias2 = a.p(f"encoders.{i}.layer_out.bias") if enc.layer_out.bias is not None else None
+              L.gemm(R, self.latent, h, ws["D"][i], 0, self.wp(self.w2[i]), 0, C_ptr=fptr(ws["Ecat"], i * self.Lp),
+                     ldc=self.n * self.Lp, bias=bias2, out=E_p)
+        self._join()
         if self.fused:
             L.gemm(R, self.latent, self.n * self.Lp, ws["Ecat_p"], 0, self.wf_planes(), 0, C_ptr=ws["F"].data_ptr(),
                    ldc=self.Lp, bias=a.p("fusion_block.bias"), out=ws["F_p"])
@@ -432,39 +459,42 @@ class TrunkEngine:
         B, Bp, R, G = ws["B"], ws["Bp"], ws["R"], self.G
         tags = [""] if G == 1 else ["anchor.", "positive.", "negative."]
         Lt, Lp = self.latent, self.Lp
+        self._fork()
         for i in range(self.n):
-            enc = model.encoders[i]
-            h, hp = self.h[i], pad8(self.h[i])
-            dE = ws["dEcat_p"].cols_view(i * Lp, Lt)
-            E_p = ws["Ecat_p"].cols_view(i * Lp, Lt)
-            has_b2 = enc.layer_out.bias is not None
-            if self.fused:
-                # dE_i = dF * Wf[:, iL:(i+1)L]   (+ column sums -> d layer_out.bias)
-                L.gemm(R, Lt, Lt, ws["dF_p"], 0, self.wf_planes(i), 1, out=dE,
-                       colstats=a.g(f"encoders.{i}.layer_out.bias") if has_b2 else None, stats_mode=3)
-                # dWf[:, iL:(i+1)L] = dF^T * E_i
-                L.gemm(Lt, Lt, R, ws["dF_p"], 1, E_p, 1, C_ptr=fptr(a.grad, a.offset["fusion_block.weight"] + i * Lt),
-                       ldc=self.n * Lt, splitk=-1)
-            # dD_i = dE_i * W2_i ; dW2_i = dE_i^T * D_i
-            L.gemm(R, h, Lt, dE, 0, self.wp(self.w2[i]), 1, C_ptr=ws["dD"][i].data_ptr(), ldc=hp)
-            L.gemm(Lt, h, R, dE, 1, ws["D"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_out.weight"), ldc=h, splitk=-1)
-            for g in range(G):
-                r0 = g * Bp
-                mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
-                dz = ws["dZ"][i].rows_view(r0, B)
-                first = g == 0
-                L.bn_bwd(V=fptr(ws["Z"][i], r0 * hp), ldv=hp, dOut=fptr(ws["dD"][i], r0 * hp), ldg=hp, rows=B, cols=h,
-                         gamma=a.p(f"encoders.{i}.batchnorm.weight"), beta=a.p(f"encoders.{i}.batchnorm.bias"),
-                         saved=ws["saved"][i][g].data_ptr(), act=1, p_drop=0.1,
-                         mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
-                         seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=a.step.data_ptr(), pre_act=0,
-                         sums=ws["sums"][i][g].data_ptr(),
-                         dgamma=a.g(f"encoders.{i}.batchnorm.weight"), dbeta=a.g(f"encoders.{i}.batchnorm.bias"),
-                         accumulate_affine=0 if first else 1,   # affine grads add up over the three triplet passes
-                         dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
-            # dW1_i = dZ_i^T * X_i
-            L.gemm(h, self.d[i], R, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_1.weight"),
-                   ldc=self.d[i], splitk=-1)
+          with torch.cuda.stream(self._stream_for(i)):
+              enc = model.encoders[i]
+              h, hp = self.h[i], pad8(self.h[i])
+              dE = ws["dEcat_p"].cols_view(i * Lp, Lt)
+              E_p = ws["Ecat_p"].cols_view(i * Lp, Lt)
+              has_b2 = enc.layer_out.bias is not None
+              if self.fused:
+                  # dE_i = dF * Wf[:, iL:(i+1)L]   (+ column sums -> d layer_out.bias)
+                  L.gemm(R, Lt, Lt, ws["dF_p"], 0, self.wf_planes(i), 1, out=dE,
+                         colstats=a.g(f"encoders.{i}.layer_out.bias") if has_b2 else None, stats_mode=3)
+                  # dWf[:, iL:(i+1)L] = dF^T * E_i
+                  L.gemm(Lt, Lt, R, ws["dF_p"], 1, E_p, 1, C_ptr=fptr(a.grad, a.offset["fusion_block.weight"] + i * Lt),
+                         ldc=self.n * Lt, splitk=-1)
+              # dD_i = dE_i * W2_i ; dW2_i = dE_i^T * D_i
+              L.gemm(R, h, Lt, dE, 0, self.wp(self.w2[i]), 1, C_ptr=ws["dD"][i].data_ptr(), ldc=hp)
+              L.gemm(Lt, h, R, dE, 1, ws["D"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_out.weight"), ldc=h, splitk=-1)
+              for g in range(G):
+                  r0 = g * Bp
+                  mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
+                  dz = ws["dZ"][i].rows_view(r0, B)
+                  first = g == 0
+                  L.bn_bwd(V=fptr(ws["Z"][i], r0 * hp), ldv=hp, dOut=fptr(ws["dD"][i], r0 * hp), ldg=hp, rows=B, cols=h,
+                           gamma=a.p(f"encoders.{i}.batchnorm.weight"), beta=a.p(f"encoders.{i}.batchnorm.bias"),
+                           saved=ws["saved"][i][g].data_ptr(), act=1, p_drop=0.1,
+                           mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
+                           seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=a.step.data_ptr(), pre_act=0,
+                           sums=ws["sums"][i][g].data_ptr(),
+                           dgamma=a.g(f"encoders.{i}.batchnorm.weight"), dbeta=a.g(f"encoders.{i}.batchnorm.bias"),
+                           accumulate_affine=0 if first else 1,   # affine grads add up over the three triplet passes
+                           dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+              # dW1_i = dZ_i^T * X_i
+              L.gemm(h, self.d[i], R, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_1.weight"),
+                     ldc=self.d[i], splitk=-1)
+        self._join()
 
     # -- optimizer --
     def optimizer_step(self, lr: float, max_norm: float = 1.0, grad_scale: float = 1.0):
