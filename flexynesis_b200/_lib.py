@@ -31,6 +31,8 @@ class GemmDesc(C.Structure):
         ("epi_act", C.c_int), ("accumulate", C.c_int),
         ("alpha", C.c_float), ("alpha_dev", C.c_void_p),
         ("mse_x", C.c_void_p), ("ldx", c_ll), ("mse_acc", C.c_void_p),
+        ("gauss_ra", C.c_void_p), ("gauss_rb", C.c_void_p), ("gauss_inv", C.c_float),
+        ("stats_alpha", C.c_float), ("stats_alpha_dev", C.c_void_p),
     ]
 
 
@@ -82,7 +84,8 @@ SYMBOLS = [
     "fxn_version", "fxn_last_error", "fxn_launch_count", "fxn_reset_launch_count", "fxn_split_planes", "fxn_gemm",
     "fxn_gemm_stat_tiles", "fxn_bn_act_fwd", "fxn_bn_act_bwd", "fxn_col_stats", "fxn_head_out_fwd", "fxn_head_out_bwd",
     "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
-    "fxn_split_planes_multi", "fxn_gather_rows",
+    "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
+    "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights",
 ]
 
 
@@ -170,7 +173,8 @@ def split_planes(src: torch.Tensor, dst: Planes) -> None:
 
 def gemm(M, N, K, a: Planes, a_mn, b: Planes, b_mn, *, C_ptr=None, ldc=0, bias=None, out: Planes = None,
          colstats=None, stats_mode=0, splitk=0, nterms=3, block_n=0, epi_act=0, accumulate=False, alpha=0.0,
-         alpha_dev=None, mse_x=None, ldx=0, mse_acc=None) -> None:
+         alpha_dev=None, mse_x=None, ldx=0, mse_acc=None, gauss_ra=None, gauss_rb=None, gauss_inv=0.0,
+         stats_alpha=0.0, stats_alpha_dev=None) -> None:
     d = GemmDesc()
     d.M, d.N, d.K = int(M), int(N), int(K)
     d.a_hi, d.a_lo, d.lda, d.a_mn_major = a.hi_ptr, a.lo_ptr, a.ld, int(a_mn)
@@ -185,6 +189,8 @@ def gemm(M, N, K, a: Planes, a_mn, b: Planes, b_mn, *, C_ptr=None, ldc=0, bias=N
     d.epi_act, d.accumulate = epi_act, int(accumulate)
     d.alpha, d.alpha_dev = alpha, alpha_dev
     d.mse_x, d.ldx, d.mse_acc = mse_x, int(ldx), mse_acc
+    d.gauss_ra, d.gauss_rb, d.gauss_inv = gauss_ra, gauss_rb, gauss_inv
+    d.stats_alpha, d.stats_alpha_dev = stats_alpha, stats_alpha_dev
     check(lib.fxn_gemm(C.byref(d), C.c_void_p(stream())), "fxn_gemm")
 
 
@@ -265,3 +271,38 @@ def gather_rows(src, ld_src, idx, nrows, cols, out, ldo, planes: "Planes" = None
                               c_ll(ldo), C.c_void_p(planes.hi_ptr if planes else None),
                               C.c_void_p(planes.lo_ptr if planes else None), c_ll(planes.ld if planes else 0),
                               C.c_void_p(stream())), "fxn_gather_rows")
+
+
+def reparam_fwd(mean, s, eps, ld, rows, cols, z, zp: "Planes") -> None:
+    check(lib.fxn_reparam_fwd(C.c_void_p(mean), C.c_void_p(s), C.c_void_p(eps), c_ll(ld), c_ll(rows), C.c_int(cols),
+                              C.c_void_p(z), C.c_void_p(zp.hi_ptr), C.c_void_p(zp.lo_ptr), c_ll(zp.ld),
+                              C.c_void_p(stream())), "fxn_reparam_fwd")
+
+
+def reparam_bwd(dz, eps, ld, rows, cols, dm: "Planes", dsp: "Planes", dbias_mean, dbias_s) -> None:
+    check(lib.fxn_reparam_bwd(C.c_void_p(dz), C.c_void_p(eps), c_ll(ld), c_ll(rows), C.c_int(cols),
+                              C.c_void_p(dm.hi_ptr), C.c_void_p(dm.lo_ptr), C.c_void_p(dsp.hi_ptr),
+                              C.c_void_p(dsp.lo_ptr), c_ll(dm.ld), C.c_void_p(dbias_mean), C.c_void_p(dbias_s),
+                              C.c_void_p(stream())), "fxn_reparam_bwd")
+
+
+def row_sqnorm(X, ld, rows, cols, out) -> None:
+    check(lib.fxn_row_sqnorm(C.c_void_p(X), c_ll(ld), c_ll(rows), C.c_int(cols), C.c_void_p(out), C.c_void_p(stream())),
+          "fxn_row_sqnorm")
+
+
+def mmd_finish(cs_zz, cs_tt, cs_tz, mse_acc, dims, nlayers, B, P, acc) -> None:
+    check(lib.fxn_mmd_finish(C.c_void_p(cs_zz), C.c_void_p(cs_tt), C.c_void_p(cs_tz), C.c_void_p(mse_acc),
+                             C.c_void_p(dims), C.c_int(nlayers), C.c_int(B), C.c_int(P), C.c_void_p(acc),
+                             C.c_void_p(stream())), "fxn_mmd_finish")
+
+
+def mmd_grad(z, ldz, cs_zz, KZ, cs_tz, KT, ldk, nlayers, B, Lt, P, weight, dz, ldd) -> None:
+    check(lib.fxn_mmd_grad(C.c_void_p(z), c_ll(ldz), C.c_void_p(cs_zz), C.c_void_p(KZ), C.c_void_p(cs_tz),
+                           C.c_void_p(KT), c_ll(ldk), C.c_int(nlayers), C.c_int(B), C.c_int(Lt), C.c_int(P),
+                           C.c_void_p(weight), C.c_void_p(dz), c_ll(ldd), C.c_void_p(stream())), "fxn_mmd_grad")
+
+
+def loss_weights(n, log_vars, weighting, wts) -> None:
+    check(lib.fxn_loss_weights(C.c_int(n), C.c_void_p(log_vars), C.c_int(int(weighting)), C.c_void_p(wts),
+                               C.c_void_p(stream())), "fxn_loss_weights")

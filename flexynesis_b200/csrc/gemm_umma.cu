@@ -44,6 +44,8 @@ struct GemmKernelArgs {
   int accumulate;         // C += result
   float alpha; const float* alpha_dev;
   const float* mse_x; long long ldx; float* mse_acc;   // fused sigmoid-MSE: see fxn_gemm_desc
+  const float* gauss_ra; const float* gauss_rb; float gauss_inv;   // epi_act 7: exp(-max(ra[m]+rb[n]-2acc,0)*inv)
+  float stats_alpha; const float* stats_alpha_dev;     // scale of the stats_mode 3 column sums
 };
 
 __device__ __forceinline__ float epi_activation(float x, int act) {
@@ -213,7 +215,16 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             if (n + 2 < p.N) o.z += __ldg(p.bias + n + 2);
             if (n + 3 < p.N) o.w += __ldg(p.bias + n + 3);
           }
-          if (p.epi_act) {
+          if (p.epi_act == 7) {
+            const float ra = __ldg(p.gauss_ra + min(m0 + row, p.M - 1));
+            const int n = n0 + c0 + j;
+            const float r0 = __ldg(p.gauss_rb + min(n + 0, p.N - 1)), r1 = __ldg(p.gauss_rb + min(n + 1, p.N - 1));
+            const float r2 = __ldg(p.gauss_rb + min(n + 2, p.N - 1)), r3 = __ldg(p.gauss_rb + min(n + 3, p.N - 1));
+            o.x = __expf(-fmaxf(ra + r0 - 2.f * o.x, 0.f) * p.gauss_inv);
+            o.y = __expf(-fmaxf(ra + r1 - 2.f * o.y, 0.f) * p.gauss_inv);
+            o.z = __expf(-fmaxf(ra + r2 - 2.f * o.z, 0.f) * p.gauss_inv);
+            o.w = __expf(-fmaxf(ra + r3 - 2.f * o.w, 0.f) * p.gauss_inv);
+          } else if (p.epi_act) {
             o.x = epi_activation(o.x, p.epi_act);
             o.y = epi_activation(o.y, p.epi_act);
             o.z = epi_activation(o.z, p.epi_act);
@@ -293,7 +304,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
     // ---- per-tile column statistics over the valid rows ----
+    if (p.stats_mode != 0 && p.mse_x != nullptr) asm volatile("bar.sync 1, 128;" ::: "memory");   // tile was rewritten
     if (p.stats_mode != 0) {
+      const float sscale = p.stats_alpha * (p.stats_alpha_dev ? __ldg(p.stats_alpha_dev) : 1.f);
       for (int c = et; c < ncolsv; c += EPI_THREADS) {
         float s = 0.f;
         for (int r = 0; r < mrows; ++r) s += stg[r * lds + c];
@@ -306,7 +319,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
         }
         if (p.stats_mode == 3) {
-          atomicAdd(p.colstats + n0 + c, s);     // plain column sums into a caller-zeroed [N] vector (bias gradients)
+          atomicAdd(p.colstats + n0 + c, s * sscale);   // plain column sums into a zeroed [N] vector (bias gradients)
         } else {
           float* dst = p.colstats + (static_cast<long long>(blockIdx.y) * 2) * p.N + n0 + c;
           dst[0] = s;
@@ -469,8 +482,12 @@ extern "C" int fxn_gemm(const fxn_gemm_desc* d, void* stream_) {
   p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
   p.alpha_dev = d->alpha_dev;
   p.mse_x = d->mse_x; p.ldx = d->ldx; p.mse_acc = d->mse_acc;
-  if (p.mse_x && (!p.mse_acc || splitk > 1 || p.stats_mode))
-    return set_error(FXN_ERR_ARG, "fxn_gemm: fused MSE needs mse_acc and excludes split-K / column stats");
+  if (p.mse_x && (!p.mse_acc || splitk > 1 || (p.stats_mode && p.stats_mode != 3)))
+    return set_error(FXN_ERR_ARG, "fxn_gemm: fused MSE needs mse_acc and excludes split-K / per-tile statistics");
+  p.gauss_ra = d->gauss_ra; p.gauss_rb = d->gauss_rb; p.gauss_inv = d->gauss_inv;
+  if (p.epi_act == 7 && (!p.gauss_ra || !p.gauss_rb)) return set_error(FXN_ERR_ARG, "fxn_gemm: epi_act 7 needs row norms");
+  p.stats_alpha = d->stats_alpha == 0.f ? 1.f : d->stats_alpha;
+  p.stats_alpha_dev = d->stats_alpha_dev;
   if (splitk > 1 && (p.epi_act || p.accumulate))
     return set_error(FXN_ERR_ARG, "fxn_gemm: split-K excludes epilogue activation / accumulate");
 

@@ -67,7 +67,7 @@ typedef struct fxn_gemm_desc {
                               plain column sums by atomics (bias gradients) */
   int splitk;              /* >1: split K over blockIdx.z, fp32 atomics into C (C is zeroed by the call); <0: auto */
   int block_n;             /* 0 = auto */
-  int epi_act;             /* applied after alpha and bias: 0 none, 1 relu, 3 sigmoid, 6 leaky_relu(0.2) */
+  int epi_act;             /* applied after alpha and bias: 0 none, 1 relu, 3 sigmoid, 6 leaky_relu(0.2), 7 Gaussian kernel */
   int accumulate;          /* C += result instead of C = result */
   float alpha;             /* result scale (0 means 1) ... */
   const float* alpha_dev;  /* ... times *alpha_dev when not NULL (device scalar, e.g. a loss weight) */
@@ -76,6 +76,11 @@ typedef struct fxn_gemm_desc {
    * to *mse_acc and the planes (c_hi, c_lo) receive G = (x_hat - x) * x_hat * (1 - x_hat) -- the gradient of the
    * squared error w.r.t. the pre-sigmoid output up to the constant 2/(M*N). C (if given) still receives x_hat. */
   const float* mse_x; long long ldx; float* mse_acc;
+  /* epi_act = 7: Gaussian kernel of compute_kernel (supervised_vae.py:494-513) from the Gram GEMM:
+   * out[m,n] = exp(-max(ra[m] + rb[n] - 2 * acc[m,n], 0) * gauss_inv), ra / rb = squared row norms of A / B. */
+  const float* gauss_ra; const float* gauss_rb; float gauss_inv;
+  /* stats_mode 3 column sums are multiplied by stats_alpha (0 means 1) * *stats_alpha_dev (if not NULL) */
+  float stats_alpha; const float* stats_alpha_dev;
 } fxn_gemm_desc;
 int fxn_gemm(const fxn_gemm_desc* d, void* stream);
 int fxn_gemm_stat_tiles(int M);
@@ -158,6 +163,30 @@ int fxn_triplet_fwd(const float* A, const float* P, const float* N, long long ld
 int fxn_triplet_bwd(const float* A, const float* P, const float* N, long long ld, int rows, int L,
                     const float* rowloss, const float* weight, float* dA, float* dP, float* dN, long long ldg,
                     int accumulate_a, void* stream);
+
+/* ---- supervised_vae latent + MMD (flexynesis/models/supervised_vae.py) ----
+ * reparameterization (:187-200): z = mean + s * eps  (s is the raw FC_log_var output, no exp). z as fp32 + planes. */
+int fxn_reparam_fwd(const float* mean, const float* s, const float* eps, long long ld, long long rows, int cols,
+                    float* z, void* z_hi, void* z_lo, long long ldp, void* stream);
+/* dmean = dz, ds = dz * eps as planes; their column sums (bias gradients of FC_mean / FC_log_var) into dbias_mean /
+ * dbias_s (zeroed by the call). */
+int fxn_reparam_bwd(const float* dz, const float* eps, long long ld, long long rows, int cols, void* dm_hi, void* dm_lo,
+                    void* ds_hi, void* ds_lo, long long ldp, float* dbias_mean, float* dbias_s, void* stream);
+/* out[r] = sum_c X[r,c]^2 */
+int fxn_row_sqnorm(const float* X, long long ld, long long rows, int cols, float* out, void* stream);
+/* MMD_loss (:532-550) assembled from column sums of the three Gaussian kernel matrices and the fused reconstruction
+ * error: loss_i = sum(cs_tt_i)/P^2 + sum(cs_zz)/B^2 - 2 sum(cs_tz_i)/(P B) + mse_acc[i]/(B d_i); acc[0] = mean_i loss_i,
+ * acc[1] = 1. cs_tt [n][P], cs_tz [n][B], dims [n] (device int32). */
+int fxn_mmd_finish(const float* cs_zz, const float* cs_tt, const float* cs_tz, const float* mse_acc, const int* dims,
+                   int nlayers, int B, int P, float* acc, void* stream);
+/* dz += w * ( -(4/(B^2 L^2)) (z * cs_zz - KZ) + (1/n) sum_i -(4/(P B L^2)) (KT_i - z * cs_tz_i) ),  w = *weight.
+ * KZ [B x L] = K(z,z) Z, KT [n][B x L] = K(t_i,z)^T T_i. */
+int fxn_mmd_grad(const float* z, long long ldz, const float* cs_zz, const float* KZ, const float* cs_tz,
+                 const float* KT, long long ldk, int nlayers, int B, int L, int P, const float* weight, float* dz,
+                 long long ldd, void* stream);
+/* wts[k] = weighting && n > 1 ? exp(-*log_vars[k]) : 1 -- the d total / d loss_k factors, available before the
+ * forward pass (they depend on parameters only). */
+int fxn_loss_weights(int n, const float* const* log_vars, int weighting, float* wts, void* stream);
 
 /* ---- step policy ----
  * clip_grad_norm_(params, max_norm) + Adam on flat arenas (flexynesis/main.py:216-217, direct_pred.py:135-144).
