@@ -85,7 +85,7 @@ SYMBOLS = [
     "fxn_gemm_stat_tiles", "fxn_bn_act_fwd", "fxn_bn_act_bwd", "fxn_col_stats", "fxn_head_out_fwd", "fxn_head_out_bwd",
     "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
-    "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights",
+    "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn",
 ]
 
 
@@ -306,3 +306,8 @@ def mmd_grad(z, ldz, cs_zz, KZ, cs_tz, KT, ldk, nlayers, B, Lt, P, weight, dz, l
 def loss_weights(n, log_vars, weighting, wts) -> None:
     check(lib.fxn_loss_weights(C.c_int(n), C.c_void_p(log_vars), C.c_int(int(weighting)), C.c_void_p(wts),
                                C.c_void_p(stream())), "fxn_loss_weights")
+
+
+def randn(out, ld, rows, cols, seed, seed_dev=None) -> None:
+    check(lib.fxn_randn(C.c_void_p(out), c_ll(ld), c_ll(rows), C.c_int(cols), C.c_ulonglong(seed), C.c_void_p(seed_dev),
+                        C.c_void_p(stream())), "fxn_randn")

@@ -4,6 +4,7 @@
 // tensors (flexynesis/models/supervised_vae.py:494-513, > 90 % of its step time) are never materialised.
 #include "fxn_internal.h"
 #include "ptx.cuh"
+#include "rng.cuh"
 
 namespace fxn {
 
@@ -138,6 +139,28 @@ mmd_grad_kernel(const float* __restrict__ z, long long ldz, const float* __restr
   }
 }
 
+// out[r, c] ~ N(0, 1) for c < cols (pad columns up to ld are left untouched); 4 values per Philox call
+__global__ void __launch_bounds__(256)
+randn_kernel(float* __restrict__ out, long long ld, long long rows, int cols, unsigned long long seed,
+             const long long* __restrict__ seed_dev) {
+  const unsigned long long s = step_seed(seed, seed_dev);
+  const int quads = (cols + 3) / 4;
+  const long long total = rows * quads;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / quads;
+    const int c = static_cast<int>(i - r * quads) * 4;
+    const uint4 u = philox4x32(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(s),
+                               static_cast<uint32_t>(s >> 32));
+    const float2 a = box_muller(u.x, u.y), b = box_muller(u.z, u.w);
+    float* o = out + r * ld + c;
+    o[0] = a.x;
+    if (c + 1 < cols) o[1] = a.y;
+    if (c + 2 < cols) o[2] = b.x;
+    if (c + 3 < cols) o[3] = b.y;
+  }
+}
+
 __global__ void loss_weights_kernel(int n, const float* const* __restrict__ log_vars, int weighting, float* __restrict__ wts) {
   const int k = threadIdx.x;
   if (k < n) wts[k] = (weighting && n > 1) ? expf(-*log_vars[k]) : 1.f;
@@ -217,5 +240,16 @@ extern "C" int fxn_loss_weights(int n, const float* const* log_vars, int weighti
   if (weighting && n > 1 && !log_vars) return set_error(FXN_ERR_ARG, "fxn_loss_weights: weighting needs log_vars");
   loss_weights_kernel<<<1, 1024, 0, stream>>>(n, log_vars, weighting, wts);
   FXN_CHECK_LAUNCH("loss_weights");
+  return 0;
+}
+
+extern "C" int fxn_randn(float* out, long long ld, long long rows, int cols, unsigned long long seed,
+                         const void* seed_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!out || rows <= 0 || cols <= 0 || ld < cols) return set_error(FXN_ERR_ARG, "fxn_randn: bad argument");
+  int blocks = ceil_div(rows * ((cols + 3) / 4), 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  randn_kernel<<<blocks, 256, 0, stream>>>(out, ld, rows, cols, seed, static_cast<const long long*>(seed_dev));
+  FXN_CHECK_LAUNCH("randn");
   return 0;
 }

@@ -301,41 +301,32 @@ class HeadsBlock:
 # ----------------------------------------------------------------------------------------------------
 # DirectPred / MultiTripletNetwork
 # ----------------------------------------------------------------------------------------------------
-class TrunkEngine:
-    """Per-modality MLP encoders -> concat -> fusion Linear -> heads (DirectPred), run on G row-groups at once
-    (G = 3 for the triplet network: anchor / positive / negative share every GEMM but keep separate BatchNorm
-    statistics, as three separate forward calls do in the reference)."""
+class EngineBase:
+    """State every model-family engine shares: the flat parameter arena, the weight planes, the supervisor heads,
+    side streams for independent per-modality chains, the optimizer step and the loss read-out."""
 
-    def __init__(self, model, device, groups: int = 1, extra_losses: Sequence[str] = ()):
-        self.model, self.device, self.G = model, torch.device(device), groups
+    def __init__(self, model, device, extra_losses: Sequence = ()):
+        self.model, self.device = model, torch.device(device)
         self.seed = 0x5EED
         self.arena = ParamArena(model, self.device)
         self.wplanes = WeightPlanes(self.arena)
         self.latent = int(model.config["latent_dim"])
-        self.n = len(model.encoders)
-        self.d = [e.layer_1.in_features for e in model.encoders]
-        self.h = [e.layer_1.out_features for e in model.encoders]
-        Lp = pad8(self.latent)
-        self.Lp = Lp
-        self.w1 = [self.wplanes.add_matrix(f"encoders.{i}.layer_1.weight") for i in range(self.n)]
-        self.w2 = [self.wplanes.add_matrix(f"encoders.{i}.layer_out.weight") for i in range(self.n)]
-        self.fused = model.fusion_block is not None
-        if self.fused:
-            self.wf_off = self.wplanes.reserve(self.latent, self.n * Lp)
-            for i in range(self.n):
-                self.wplanes.add_segment("fusion_block.weight", i * self.latent, self.latent, self.latent,
-                                         self.n * self.latent, self.wf_off + i * Lp, self.n * Lp)
-        self.heads = HeadsBlock(self, model, extra_losses)
+        self.Lp = pad8(self.latent)
+        self._extra_losses = extra_losses
+        self.inputs = InputCache()
+        self.ws: Dict[int, dict] = {}
+        self.side: List[torch.cuda.Stream] = []
+        self.parallel_encoders = True
+
+    def _finish_init(self, n_side: int):
+        """Call at the end of a subclass constructor, after every weight plane has been registered."""
+        self.heads = HeadsBlock(self, self.model, self._extra_losses)
         self.wplanes.finalize()
         self.wplanes.refresh()
         self._versions = self.arena.versions()
-        self.inputs = InputCache()
-        self.ws: Dict[int, dict] = {}
-        # the per-modality encoder chains are independent until the fusion GEMM: run them on parallel streams (they
-        # become parallel branches of the captured CUDA graph) so that small tiles of one modality fill the SMs the
-        # other leaves idle
-        self.side = [torch.cuda.Stream(device=self.device) for _ in range(max(self.n - 1, 0))]
-        self.parallel_encoders = True
+        # independent per-modality chains run on parallel streams (they become parallel branches of the captured
+        # CUDA graph) so that small tiles of one modality fill the SMs the other leaves idle
+        self.side = [torch.cuda.Stream(device=self.device) for _ in range(max(n_side, 0))]
 
     # -- helpers --
     def _stream_for(self, i: int):
@@ -369,6 +360,57 @@ class TrunkEngine:
     def wp(self, t) -> Planes:
         _, off, rows, cols, ld = t
         return self.wplanes.planes(off, rows, cols, ld)
+
+    def optimizer_step(self, lr: float, max_norm: float = 1.0, grad_scale: float = 1.0):
+        a = self.arena
+        L.clip_adam(a.flat.data_ptr(), a.grad.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(), a.numel, lr,
+                    max_norm, grad_scale, a.sumsq.data_ptr(), a.step.data_ptr(), a.grad_norm.data_ptr())
+        self.wplanes.refresh()
+
+    def _labels(self, y: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        out = {}
+        for k, v in y.items():
+            if not torch.is_tensor(v):
+                continue
+            if v.device != self.device or v.dtype != torch.float32 or not v.is_contiguous():
+                v = v.to(self.device, torch.float32).contiguous()
+            out[k] = v
+        return out
+
+    def _input(self, x: torch.Tensor) -> torch.Tensor:
+        if x.device != self.device or x.dtype != torch.float32:
+            x = x.to(self.device, torch.float32)
+        return x.contiguous() if x.stride(-1) != 1 else x
+
+    def losses(self, ws) -> Dict[str, torch.Tensor]:
+        out = ws["heads"]["out"]
+        n = self.heads.n_losses
+        res = {name: out[i] for i, name in enumerate(self.heads.loss_names)}
+        res["__total__"], res["__val_total__"] = out[n], out[n + 1]
+        return res
+
+
+class TrunkEngine(EngineBase):
+    """Per-modality MLP encoders -> concat -> fusion Linear -> heads (DirectPred), run on G row-groups at once
+    (G = 3 for the triplet network: anchor / positive / negative share every GEMM but keep separate BatchNorm
+    statistics, as three separate forward calls do in the reference)."""
+
+    def __init__(self, model, device, groups: int = 1, extra_losses: Sequence = ()):
+        super().__init__(model, device, extra_losses)
+        self.G = groups
+        self.n = len(model.encoders)
+        self.d = [e.layer_1.in_features for e in model.encoders]
+        self.h = [e.layer_1.out_features for e in model.encoders]
+        Lp = self.Lp
+        self.w1 = [self.wplanes.add_matrix(f"encoders.{i}.layer_1.weight") for i in range(self.n)]
+        self.w2 = [self.wplanes.add_matrix(f"encoders.{i}.layer_out.weight") for i in range(self.n)]
+        self.fused = model.fusion_block is not None
+        if self.fused:
+            self.wf_off = self.wplanes.reserve(self.latent, self.n * Lp)
+            for i in range(self.n):
+                self.wplanes.add_segment("fusion_block.weight", i * self.latent, self.latent, self.latent,
+                                         self.n * self.latent, self.wf_off + i * Lp, self.n * Lp)
+        self._finish_init(self.n - 1)
 
     def wf_planes(self, i: Optional[int] = None) -> Planes:
         full = self.wplanes.planes(self.wf_off, self.latent, self.n * self.Lp, self.n * self.Lp)
@@ -496,25 +538,7 @@ class TrunkEngine:
                      ldc=self.d[i], splitk=-1)
         self._join()
 
-    # -- optimizer --
-    def optimizer_step(self, lr: float, max_norm: float = 1.0, grad_scale: float = 1.0):
-        a = self.arena
-        L.clip_adam(a.flat.data_ptr(), a.grad.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(), a.numel, lr,
-                    max_norm, grad_scale, a.sumsq.data_ptr(), a.step.data_ptr(), a.grad_norm.data_ptr())
-        self.wplanes.refresh()
-
-
     # -- full steps --
-    def _labels(self, y: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        out = {}
-        for k, v in y.items():
-            if not torch.is_tensor(v):
-                continue
-            if v.device != self.device or v.dtype != torch.float32 or not v.is_contiguous():
-                v = v.to(self.device, torch.float32).contiguous()
-            out[k] = v
-        return out
-
     def forward_backward(self, x_groups, y, masks=None):
         """One training forward + backward. x_groups: G lists of per-layer [B x d] fp32 tensors. Fills arena.grad and
         returns the heads workspace (loss values in ws['out'], logits in ws['logits'])."""
@@ -576,9 +600,275 @@ class TrunkEngine:
         B, Bp = ws["B"], ws["Bp"]
         return ws["F"][group * Bp:group * Bp + B, :self.latent]
 
-    def losses(self, ws) -> Dict[str, torch.Tensor]:
-        out = ws["heads"]["out"]
-        n = self.heads.n_losses
-        res = {name: out[i] for i, name in enumerate(self.heads.loss_names)}
-        res["__total__"], res["__val_total__"] = out[n], out[n + 1]
-        return res
+
+# ----------------------------------------------------------------------------------------------------
+# supervised_vae
+# ----------------------------------------------------------------------------------------------------
+class VAEEngine(EngineBase):
+    """supervised_vae (flexynesis/models/supervised_vae.py): per-modality Encoder (Linear -> LeakyReLU(0.2) -> BN ->
+    FC_mean | FC_var), FC_mean / FC_log_var over the concatenations, z = mean + s * eps, per-modality Decoder with the
+    sigmoid + reconstruction error fused into the output GEMM, heads on z, and the MMD term evaluated through Gram
+    GEMMs with a Gaussian-kernel epilogue (the reference's [B, B, L] broadcast tensors are never formed).
+
+    Noise replay (tests): the `masks` dict may carry "epsilon" [B x L] and "mmd_prior.<i>" [200 x L] fp32 tensors next to
+    the dropout masks; anything missing is drawn on the device (Philox keyed by the step counter)."""
+
+    PRIOR = 200          # torch.randn(200, latent_dim), supervised_vae.py:545
+
+    def __init__(self, model, device):
+        super().__init__(model, device, extra_losses=(("mmd_loss", 3),))
+        a, wp = self.arena, self.wplanes
+        self.n = len(model.encoders)
+        self.d = [e.hidden_layers[0].in_features for e in model.encoders]
+        self.h = [e.hidden_layers[0].out_features for e in model.encoders]
+        Lt, Lp, n = self.latent, self.Lp, self.n
+        self.w1 = [wp.add_matrix(f"encoders.{i}.hidden_layers.0.weight") for i in range(n)]
+        self.wm = [wp.add_matrix(f"encoders.{i}.FC_mean.weight") for i in range(n)]
+        self.wv = [wp.add_matrix(f"encoders.{i}.FC_var.weight") for i in range(n)]
+        self.wd = [wp.add_matrix(f"decoders.{i}.hidden_layers.0.weight") for i in range(n)]
+        self.wo = [wp.add_matrix(f"decoders.{i}.FC_output.weight") for i in range(n)]
+        # FC_mean / FC_log_var weights [L x n*L] as planes [L x n*Lp]: block i at columns [i*Lp, i*Lp + L)
+        self.wfc_off = {}
+        for name in ("FC_mean", "FC_log_var"):
+            off = wp.reserve(Lt, n * Lp)
+            for i in range(n):
+                wp.add_segment(f"{name}.weight", i * Lt, Lt, Lt, n * Lt, off + i * Lp, n * Lp)
+            self.wfc_off[name] = off
+        self._finish_init(n)          # n - 1 modality streams + one for the heads / MMD chain
+        self.dims_dev = torch.tensor(self.d, dtype=torch.int32, device=self.device)
+        self.mmd_slot = self.heads.loss_names.index("mmd_loss")
+
+    def _aux_stream(self):
+        return self.side[-1] if self.parallel_encoders else torch.cuda.current_stream()
+
+    def wfc(self, name: str, i: Optional[int] = None) -> Planes:
+        full = self.wplanes.planes(self.wfc_off[name], self.latent, self.n * self.Lp, self.n * self.Lp)
+        return full if i is None else full.cols_view(i * self.Lp, self.latent)
+
+    def workspace(self, B: int) -> dict:
+        if B in self.ws:
+            return self.ws[B]
+        dev, n, Lt, Lp, P = self.device, self.n, self.latent, self.Lp, self.PRIOR
+        mt = L.stat_tiles(B)
+        f = lambda *shape: torch.zeros(*shape, device=dev)
+        ws = dict(B=B)
+        ws["X"] = [Planes.empty(B, self.d[i], dev) for i in range(n)]
+        ws["x_f32"] = [None] * n
+        for tag in ("", "d"):     # encoder / decoder hidden blocks
+            ws["A" + tag] = [f(B, pad8(self.h[i])) for i in range(n)]
+            ws["Y" + tag] = [Planes.empty(B, self.h[i], dev) for i in range(n)]
+            ws["partials" + tag] = [f(mt * 2 * self.h[i]) for i in range(n)]
+            ws["saved" + tag] = [f(2 * self.h[i]) for i in range(n)]
+            ws["sums" + tag] = [f(2 * self.h[i]) for i in range(n)]
+            ws["dY" + tag] = [f(B, pad8(self.h[i])) for i in range(n)]
+            ws["dZ" + tag] = [Planes.empty(B, self.h[i], dev) for i in range(n)]
+        ws["Mcat_p"] = Planes.empty(B, n * Lp, dev, ld=n * Lp)
+        ws["Vcat_p"] = Planes.empty(B, n * Lp, dev, ld=n * Lp)
+        for k in ("mean", "s", "eps", "z", "dz", "KZ"):
+            ws[k] = f(B, Lp)
+        ws["z_p"] = Planes.empty(B, Lt, dev, ld=Lp)
+        ws["dm_p"] = Planes.empty(B, Lt, dev, ld=Lp)
+        ws["ds_p"] = Planes.empty(B, Lt, dev, ld=Lp)
+        ws["dM_p"] = [Planes.empty(B, Lt, dev, ld=Lp) for _ in range(n)]
+        ws["dV_p"] = [Planes.empty(B, Lt, dev, ld=Lp) for _ in range(n)]
+        ws["G"] = [Planes.empty(B, self.d[i], dev) for i in range(n)]
+        ws["xhat"] = [None] * n
+        ws["mse_acc"] = f(n)
+        ws["wts"] = f(max(self.heads.n_losses, 1))
+        # MMD
+        ws["T"] = [f(P, Lp) for _ in range(n)]
+        ws["T_p"] = [Planes.empty(P, Lt, dev, ld=Lp) for _ in range(n)]
+        ws["rz"], ws["rt"] = f(B), [f(P) for _ in range(n)]
+        ws["Kzz_p"] = Planes.empty(B, B, dev)
+        ws["Ktz_p"] = [Planes.empty(P, B, dev) for _ in range(n)]
+        ws["Ktt_p"] = Planes.empty(P, P, dev)
+        ws["cs_zz"], ws["cs_tz"], ws["cs_tt"] = f(B), f(n, B), f(n, P)
+        ws["KT"] = f(n, B, Lp)
+        ws["heads"] = self.heads.workspace(B)
+        self.ws[B] = ws
+        return ws
+
+    def stage_inputs(self, ws, x_list: Sequence[torch.Tensor]):
+        for i, x in enumerate(x_list):
+            x = self._input(x)
+            ws["x_f32"][i] = x                      # the reconstruction error reads the fp32 input
+            self.inputs.get((ws["B"], i), x, ws["X"][i])
+
+    def _hidden_fwd(self, ws, tag: str, i: int, prefix: str, inp: Planes, K: int, wplanes: Planes, train: bool):
+        """Linear -> LeakyReLU(0.2) (GEMM epilogue) -> BatchNorm1d; returns nothing, fills A/Y/saved."""
+        a = self.arena
+        B, h, hp = ws["B"], self.h[i], pad8(self.h[i])
+        A, Y = ws["A" + tag][i], ws["Y" + tag][i]
+        bn = self.model.get_submodule(prefix).hidden_layers[2]
+        L.gemm(B, h, K, inp, 0, wplanes, 0, C_ptr=A.data_ptr(), ldc=hp, bias=a.p(f"{prefix}.hidden_layers.0.bias"),
+               epi_act=6, colstats=ws["partials" + tag][i].data_ptr() if train else None, stats_mode=2)
+        L.bn_fwd(V=A.data_ptr(), ldv=hp, rows=B, cols=h, partials=ws["partials" + tag][i].data_ptr(),
+                 ntiles=L.stat_tiles(B), tile_rows=128, gamma=a.p(f"{prefix}.hidden_layers.2.weight"),
+                 beta=a.p(f"{prefix}.hidden_layers.2.bias"), momentum=MOMENTUM, eps=EPS, train=int(train), act=0,
+                 p_drop=0.0, out_hi=Y.hi_ptr, out_lo=Y.lo_ptr, ldp=Y.ld, saved=ws["saved" + tag][i].data_ptr(),
+                 **_bn_ptrs(bn))
+
+    def _hidden_bwd(self, ws, tag: str, i: int, prefix: str):
+        """BatchNorm backward + LeakyReLU derivative: dY (fp32) -> dZ planes; fills d gamma / beta / bias."""
+        a = self.arena
+        B, h, hp = ws["B"], self.h[i], pad8(self.h[i])
+        dz = ws["dZ" + tag][i]
+        L.bn_bwd(V=ws["A" + tag][i].data_ptr(), ldv=hp, dOut=ws["dY" + tag][i].data_ptr(), ldg=hp, rows=B, cols=h,
+                 gamma=a.p(f"{prefix}.hidden_layers.2.weight"), beta=a.p(f"{prefix}.hidden_layers.2.bias"),
+                 saved=ws["saved" + tag][i].data_ptr(), act=0, p_drop=0.0, pre_act=1,
+                 sums=ws["sums" + tag][i].data_ptr(), dgamma=a.g(f"{prefix}.hidden_layers.2.weight"),
+                 dbeta=a.g(f"{prefix}.hidden_layers.2.bias"), dbias=a.g(f"{prefix}.hidden_layers.0.bias"),
+                 dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+
+    # ---- forward: encoders -> latent -> decoders | heads | MMD ----
+    def _forward(self, ws, y, train: bool, noise, with_loss: bool, want_xhat: bool = False):
+        a, hw = self.arena, ws["heads"]
+        B, n, Lt, Lp, P = ws["B"], self.n, self.latent, self.Lp, self.PRIOR
+        noise = noise or {}
+        hw["acc"].zero_()
+        ws["mse_acc"].zero_()
+        hb = self.heads
+        L.loss_weights(hb.n_losses, None if hb.lv_dev is None else hb.lv_dev.data_ptr(), hb.weighting,
+                       ws["wts"].data_ptr())
+        w_mmd = fptr(ws["wts"], self.mmd_slot)
+        self._fork()
+        for i in range(n):
+            with torch.cuda.stream(self._stream_for(i)):
+                self._hidden_fwd(ws, "", i, f"encoders.{i}", ws["X"][i], self.d[i], self.wp(self.w1[i]), train)
+                L.gemm(B, Lt, self.h[i], ws["Y"][i], 0, self.wp(self.wm[i]), 0, bias=a.p(f"encoders.{i}.FC_mean.bias"),
+                       out=ws["Mcat_p"].cols_view(i * Lp, Lt))
+                L.gemm(B, Lt, self.h[i], ws["Y"][i], 0, self.wp(self.wv[i]), 0, bias=a.p(f"encoders.{i}.FC_var.bias"),
+                       out=ws["Vcat_p"].cols_view(i * Lp, Lt))
+        self._join()
+        L.gemm(B, Lt, n * Lp, ws["Mcat_p"], 0, self.wfc("FC_mean"), 0, C_ptr=ws["mean"].data_ptr(), ldc=Lp,
+               bias=a.p("FC_mean.bias"))
+        L.gemm(B, Lt, n * Lp, ws["Vcat_p"], 0, self.wfc("FC_log_var"), 0, C_ptr=ws["s"].data_ptr(), ldc=Lp,
+               bias=a.p("FC_log_var.bias"))
+        if "epsilon" in noise:
+            ws["eps"][:, :Lt].copy_(noise["epsilon"])
+        else:
+            L.randn(ws["eps"].data_ptr(), Lp, B, Lt, self.seed + 11, a.step.data_ptr())
+        L.reparam_fwd(ws["mean"].data_ptr(), ws["s"].data_ptr(), ws["eps"].data_ptr(), Lp, B, Lt, ws["z"].data_ptr(),
+                      ws["z_p"])
+        # decoders, and beside them (aux stream) the heads and the MMD chain
+        self._fork()
+        for i in range(n):
+            with torch.cuda.stream(self._stream_for(i)):
+                self._hidden_fwd(ws, "d", i, f"decoders.{i}", ws["z_p"], Lt, self.wp(self.wd[i]), train)
+                x = ws["x_f32"][i]
+                if want_xhat and ws["xhat"][i] is None:
+                    ws["xhat"][i] = torch.zeros(B, self.d[i], device=self.device)
+                scale = 2.0 / (float(B) * self.d[i] * n)
+                L.gemm(B, self.d[i], self.h[i], ws["Yd"][i], 0, self.wp(self.wo[i]), 0,
+                       C_ptr=ws["xhat"][i].data_ptr() if want_xhat else None, ldc=self.d[i],
+                       bias=a.p(f"decoders.{i}.FC_output.bias"), epi_act=3, out=ws["G"][i],
+                       mse_x=x.data_ptr(), ldx=x.stride(0), mse_acc=fptr(ws["mse_acc"], i),
+                       colstats=a.g(f"decoders.{i}.FC_output.bias") if train else None, stats_mode=3,
+                       stats_alpha=scale, stats_alpha_dev=w_mmd)
+        with torch.cuda.stream(self._aux_stream()):
+            self._heads_and_mmd(ws, y, train, noise, with_loss)
+        self._join()
+        if with_loss:
+            L.mmd_finish(ws["cs_zz"].data_ptr(), ws["cs_tt"].data_ptr(), ws["cs_tz"].data_ptr(),
+                         ws["mse_acc"].data_ptr(), self.dims_dev.data_ptr(), n, B, P, fptr(hw["acc"], 2 * self.mmd_slot))
+            hb.total(hw)
+
+    def _heads_and_mmd(self, ws, y, train, noise, with_loss):
+        a, hw, hb = self.arena, ws["heads"], self.heads
+        B, n, Lt, Lp, P = ws["B"], self.n, self.latent, self.Lp, self.PRIOR
+        hb.forward(hw, ws["z_p"], B, y, train, noise, with_loss=with_loss)
+        if with_loss:
+            # MMD: Gaussian-kernel Gram matrices + column sums
+            inv = 1.0 / (float(Lt) * float(Lt))
+            L.row_sqnorm(ws["z"].data_ptr(), Lp, B, Lt, ws["rz"].data_ptr())
+            L.gemm(B, B, Lt, ws["z_p"], 0, ws["z_p"], 0, out=ws["Kzz_p"], epi_act=7, gauss_ra=ws["rz"].data_ptr(),
+                   gauss_rb=ws["rz"].data_ptr(), gauss_inv=inv, colstats=ws["cs_zz"].data_ptr(), stats_mode=3)
+            for i in range(n):
+                T = ws["T"][i]
+                if f"mmd_prior.{i}" in noise:
+                    T[:, :Lt].copy_(noise[f"mmd_prior.{i}"])
+                else:
+                    L.randn(T.data_ptr(), Lp, P, Lt, self.seed + 101 + i, a.step.data_ptr())
+                L.split_planes(T[:, :Lt], ws["T_p"][i])
+                L.row_sqnorm(T.data_ptr(), Lp, P, Lt, ws["rt"][i].data_ptr())
+                L.gemm(P, B, Lt, ws["T_p"][i], 0, ws["z_p"], 0, out=ws["Ktz_p"][i], epi_act=7,
+                       gauss_ra=ws["rt"][i].data_ptr(), gauss_rb=ws["rz"].data_ptr(), gauss_inv=inv,
+                       colstats=ws["cs_tz"][i].data_ptr(), stats_mode=3)
+                L.gemm(P, P, Lt, ws["T_p"][i], 0, ws["T_p"][i], 0, out=ws["Ktt_p"], epi_act=7,
+                       gauss_ra=ws["rt"][i].data_ptr(), gauss_rb=ws["rt"][i].data_ptr(), gauss_inv=inv,
+                       colstats=ws["cs_tt"][i].data_ptr(), stats_mode=3)
+
+    def forward_backward(self, x_groups, y, masks=None):
+        x_list = x_groups[0]
+        B = x_list[0].shape[0]
+        ws = self.workspace(B)
+        hw, a = ws["heads"], self.arena
+        n, Lt, Lp, P = self.n, self.latent, self.Lp, self.PRIOR
+        y = self._labels(y)
+        self.ensure_fresh()
+        self.stage_inputs(ws, x_list)
+        self._forward(ws, y, True, masks, True)
+        w_mmd = fptr(ws["wts"], self.mmd_slot)
+        # ---- backward ----
+        if not self.heads.backward(hw, ws["z_p"], B, y, masks, None, ws["dz"], None):
+            ws["dz"].zero_()
+        self._fork()
+        for i in range(n):
+            with torch.cuda.stream(self._stream_for(i)):
+                scale = 2.0 / (float(B) * self.d[i] * n)
+                h, hp, d = self.h[i], pad8(self.h[i]), self.d[i]
+                # dYd = c * G * Wo ; dWo = c * G^T * Yd         (c = 2 / (B d n) * weight of mmd_loss)
+                L.gemm(B, h, d, ws["G"][i], 0, self.wp(self.wo[i]), 1, C_ptr=ws["dYd"][i].data_ptr(), ldc=hp,
+                       alpha=scale, alpha_dev=w_mmd)
+                L.gemm(d, h, B, ws["G"][i], 1, ws["Yd"][i], 1, C_ptr=a.g(f"decoders.{i}.FC_output.weight"), ldc=h,
+                       alpha=scale, alpha_dev=w_mmd, splitk=-1)
+                self._hidden_bwd(ws, "d", i, f"decoders.{i}")
+                L.gemm(h, Lt, B, ws["dZd"][i], 1, ws["z_p"], 1, C_ptr=a.g(f"decoders.{i}.hidden_layers.0.weight"),
+                       ldc=Lt, splitk=-1)
+        with torch.cuda.stream(self._aux_stream()):      # MMD gradient operands beside the decoder chains
+            L.gemm(B, Lt, B, ws["Kzz_p"], 0, ws["z_p"], 1, C_ptr=ws["KZ"].data_ptr(), ldc=Lp)
+            for i in range(n):
+                L.gemm(B, Lt, P, ws["Ktz_p"][i], 1, ws["T_p"][i], 1, C_ptr=ws["KT"][i].data_ptr(), ldc=Lp)
+        self._join()
+        for i in range(n):
+            L.gemm(B, Lt, self.h[i], ws["dZd"][i], 0, self.wp(self.wd[i]), 1, C_ptr=ws["dz"].data_ptr(), ldc=Lp,
+                   accumulate=True)
+        L.mmd_grad(ws["z"].data_ptr(), Lp, ws["cs_zz"].data_ptr(), ws["KZ"].data_ptr(), ws["cs_tz"].data_ptr(),
+                   ws["KT"].data_ptr(), Lp, n, B, Lt, P, w_mmd, ws["dz"].data_ptr(), Lp)
+        L.reparam_bwd(ws["dz"].data_ptr(), ws["eps"].data_ptr(), Lp, B, Lt, ws["dm_p"], ws["ds_p"],
+                      a.g("FC_mean.bias"), a.g("FC_log_var.bias"))
+        self._fork()
+        for i in range(n):
+            with torch.cuda.stream(self._stream_for(i)):
+                h, hp, d = self.h[i], pad8(self.h[i]), self.d[i]
+                for name, dsrc, cat, dst, wenc, encname in (
+                        ("FC_mean", ws["dm_p"], ws["Mcat_p"], ws["dM_p"][i], self.wm[i], "FC_mean"),
+                        ("FC_log_var", ws["ds_p"], ws["Vcat_p"], ws["dV_p"][i], self.wv[i], "FC_var")):
+                    # d W_fc[:, iL:(i+1)L] = dsrc^T * cat_i
+                    L.gemm(Lt, Lt, B, dsrc, 1, cat.cols_view(i * Lp, Lt), 1,
+                           C_ptr=fptr(a.grad, a.offset[f"{name}.weight"] + i * Lt), ldc=n * Lt, splitk=-1)
+                    # d cat_i = dsrc * W_fc[:, iL:(i+1)L]   (+ column sums -> bias gradient of the encoder's FC)
+                    L.gemm(B, Lt, Lt, dsrc, 0, self.wfc(name, i), 1, out=dst,
+                           colstats=a.g(f"encoders.{i}.{encname}.bias"), stats_mode=3)
+                    # dY_i (+)= d cat_i * W_enc ; d W_enc = d cat_i^T * Y_i
+                    L.gemm(B, h, Lt, dst, 0, self.wp(wenc), 1, C_ptr=ws["dY"][i].data_ptr(), ldc=hp,
+                           accumulate=(name != "FC_mean"))
+                    L.gemm(Lt, h, B, dst, 1, ws["Y"][i], 1, C_ptr=a.g(f"encoders.{i}.{encname}.weight"), ldc=h,
+                           splitk=-1)
+                self._hidden_bwd(ws, "", i, f"encoders.{i}")
+                L.gemm(h, d, B, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.hidden_layers.0.weight"),
+                       ldc=d, splitk=-1)
+        self._join()
+        return ws
+
+    def evaluate(self, x_groups, y=None, train_mode: bool = False, masks=None, want_xhat: bool = False):
+        x_list = x_groups[0]
+        ws = self.workspace(x_list[0].shape[0])
+        self.ensure_fresh()
+        self.stage_inputs(ws, x_list)
+        yl = self._labels(y) if y is not None else None
+        self._forward(ws, yl, train_mode, masks, y is not None, want_xhat)
+        return ws
+
+    def embedding(self, ws, group: int = 0) -> torch.Tensor:
+        return ws["z"][:, :self.latent]

@@ -369,3 +369,115 @@ class MultiTripletNetwork(DirectPred):
                 names.extend(samples)
         e = torch.cat(embs, 0)
         return pd.DataFrame(e.numpy(), index=names, columns=[f"E{i}" for i in range(e.shape[1])])
+
+
+class supervised_vae(_EngineModel):
+    """MMD-regularised variational autoencoder with supervisor heads on the latent code
+    (flexynesis/models/supervised_vae.py:42-130). Constructor order of the sub-modules follows the reference so that
+    the same torch seed gives the same initial parameters."""
+
+    def __init__(self, config, dataset, target_variables, batch_variables=None, surv_event_var=None,
+                 surv_time_var=None, use_loss_weighting=True, device_type=None):
+        super().__init__()
+        self.config = config
+        self.dataset = dataset
+        self.target_variables = target_variables
+        self.surv_event_var, self.surv_time_var = surv_event_var, surv_time_var
+        if surv_event_var is not None and surv_time_var is not None:
+            self.target_variables = self.target_variables + [surv_event_var]
+        self.batch_variables = batch_variables
+        self.variables = self.target_variables + batch_variables if batch_variables else self.target_variables
+        self.feature_importances = {}
+        self.nan_detected = False
+        self.device_type = device_type
+        self.use_loss_weighting = use_loss_weighting
+        if use_loss_weighting:
+            self.log_vars = nn.ParameterDict(
+                {v: nn.Parameter(torch.zeros(1)) for v in itertools.chain(self.variables, ["mmd_loss"])})
+        self.variable_types = dataset.variable_types
+        self.layers = list(dataset.dat.keys())
+        self.input_dims = [len(dataset.features[k]) for k in self.layers]
+        latent, n = config["latent_dim"], len(self.layers)
+        hidden = [max(int(d * config["hidden_dim_factor"]), 2) for d in self.input_dims]
+        self.encoders = nn.ModuleList([Encoder(d, [h], latent) for d, h in zip(self.input_dims, hidden)])
+        self.FC_mean = nn.Linear(n * latent, latent)
+        self.FC_log_var = nn.Linear(n * latent, latent)
+        self.decoders = nn.ModuleList([Decoder(latent, [h], d) for d, h in zip(self.input_dims, hidden)])
+        self.MLPs = nn.ModuleDict()
+        for var in self.variables:
+            classes = 1 if self.variable_types[var] == "numerical" else len(np.unique(dataset.ann[var]))
+            self.MLPs[var] = MLP(latent, config["supervisor_hidden_dim"], classes)
+
+    def _make_engine(self, device):
+        from .engine import VAEEngine
+        return VAEEngine(self, device)
+
+    # ---- torch formulation (CPU-resident inference, captum) ----
+    def multi_encoder(self, x_list):
+        means, log_vars = zip(*[enc(x) for enc, x in zip(self.encoders, x_list)])
+        return self.FC_mean(torch.cat(means, dim=1)), self.FC_log_var(torch.cat(log_vars, dim=1))
+
+    def reparameterization(self, mean, var):
+        return mean + var * torch.randn_like(var)
+
+    def forward(self, x_list):
+        """(x_hat_list, z, mean, log_var, {var: head output}); epsilon is drawn in eval mode too, as in the reference
+        (supervised_vae.py:187-200)."""
+        x_list = list(x_list)
+        use_engine = all(x.is_cuda and not x.requires_grad for x in x_list) and not (
+            self.training and torch.is_grad_enabled())
+        if use_engine:
+            eng = self.engine(x_list[0].device)
+            ws = eng.evaluate([x_list], None, train_mode=self.training, want_xhat=True)
+            Lt = eng.latent
+            return ([t.clone() for t in ws["xhat"]], ws["z"][:, :Lt].clone(), ws["mean"][:, :Lt].clone(),
+                    ws["s"][:, :Lt].clone(), self._outputs_from_ws(eng, ws))
+        mean, log_var = self.multi_encoder(x_list)
+        z = self.reparameterization(mean, log_var)
+        return [dec(z) for dec in self.decoders], z, mean, log_var, {v: mlp(z) for v, mlp in self.MLPs.items()}
+
+    def compute_kernel(self, x, y):
+        dim = x.shape[1]
+        d2 = (x * x).sum(1)[:, None] + (y * y).sum(1)[None, :] - 2.0 * x @ y.T
+        return torch.exp(-d2.clamp_min(0.0) / float(dim * dim))
+
+    def compute_mmd(self, x, y):
+        return self.compute_kernel(x, x).mean() + self.compute_kernel(y, y).mean() - 2 * self.compute_kernel(x, y).mean()
+
+    def MMD_loss(self, latent_dim, z, xhat, x):
+        prior = torch.randn(200, latent_dim, device=z.device)
+        return self.compute_mmd(prior, z) + torch.mean((xhat - x) ** 2)
+
+    def _run_eval(self, dataset, want):
+        self.eval()
+        device = _resolve_device(self.device_type)
+        self.to(device)
+        out = {v: [] for v in self.variables}
+        embs, names = [], []
+        with torch.no_grad():
+            for xs, samples in self._batches(dataset, 4096 if device.type == "cuda" else 64):
+                _, z, _, _, outputs = self.forward([x.to(device, torch.float32) for x in xs])
+                embs.append(z.detach().cpu())
+                names.extend(samples)
+                for v in self.variables:
+                    o = outputs[v].detach().float().cpu()
+                    out[v].append(torch.softmax(o, dim=1) if dataset.variable_types[v] == "categorical" else o)
+        if want == "embedding":
+            e = torch.cat(embs, 0)
+            return pd.DataFrame(e.numpy(), index=names, columns=[f"E{i}" for i in range(e.shape[1])])
+        return {v: torch.cat(p).numpy() for v, p in out.items()}
+
+    def transform(self, dataset):
+        """Latent codes z as a DataFrame (supervised_vae.py:383-436)."""
+        return self._run_eval(dataset, "embedding")
+
+    def predict(self, dataset):
+        """{var: np.ndarray} (supervised_vae.py:438-492)."""
+        return self._run_eval(dataset, "predict")
+
+    def forward_target(self, *args):
+        inputs, target_var, steps = list(args[:-2]), args[-2], args[-1]
+        outs = []
+        for i in range(steps):
+            outs.append(self.forward([x[i] for x in inputs])[4][target_var])
+        return torch.cat(outs, dim=0)

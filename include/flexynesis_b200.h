@@ -172,6 +172,10 @@ int fxn_reparam_fwd(const float* mean, const float* s, const float* eps, long lo
  * dbias_s (zeroed by the call). */
 int fxn_reparam_bwd(const float* dz, const float* eps, long long ld, long long rows, int cols, void* dm_hi, void* dm_lo,
                     void* ds_hi, void* ds_lo, long long ldp, float* dbias_mean, float* dbias_s, void* stream);
+/* Standard normal draws out[r, c], c < cols (epsilon of reparameterization, torch.randn_like, :198; the MMD prior
+ * torch.randn(200, latent), :545): Philox4x32-10 + Box-Muller keyed by (seed, *seed_dev, element). */
+int fxn_randn(float* out, long long ld, long long rows, int cols, unsigned long long seed, const void* seed_dev,
+              void* stream);
 /* out[r] = sum_c X[r,c]^2 */
 int fxn_row_sqnorm(const float* X, long long ld, long long rows, int cols, float* out, void* stream);
 /* MMD_loss (:532-550) assembled from column sums of the three Gaussian kernel matrices and the fused reconstruction

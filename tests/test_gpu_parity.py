@@ -66,7 +66,14 @@ def to_cuda(batch):
 
 
 def masks_from_noise(noise):
-    return {k: (v != 0).to(torch.uint8).cuda().contiguous() for k, v in noise.items() if "dropout" in k}
+    """Replayed noise for the engine: dropout keep-masks as uint8, Gaussian draws (epsilon, MMD priors) as fp32."""
+    out = {}
+    for k, v in noise.items():
+        if "dropout" in k:
+            out[k] = (v != 0).to(torch.uint8).cuda().contiguous()
+        else:
+            out[k] = v.float().cuda().contiguous()
+    return out
 
 
 class Report:
@@ -99,6 +106,11 @@ def gate_margin_units(spec, P, batch, res, masks, margin=2e-4):
     out = {}
 
     def block(prefix, x):
+        if prefix + ".layer_1.weight" not in P:
+            # Encoder / Decoder: Linear -> LeakyReLU(0.2) -> BN; the gate sits directly on the Linear output
+            z = Fn.linear(x, P[prefix + ".hidden_layers.0.weight"], P[prefix + ".hidden_layers.0.bias"])
+            out[prefix] = z.abs().min(0).values < margin * float(z.abs().max())
+            return
         z = Fn.linear(x, P[prefix + ".layer_1.weight"], P[prefix + ".layer_1.bias"])
         yv = (z - z.mean(0)) * torch.rsqrt(z.var(0, unbiased=False) + 1e-5) * P[prefix + ".batchnorm.weight"] \
             + P[prefix + ".batchnorm.bias"]
@@ -114,6 +126,9 @@ def gate_margin_units(spec, P, batch, res, masks, margin=2e-4):
                 block(f"encoders.{i}", x)
         for v in spec.variables:
             block(f"MLPs.{v}", res["embedding"].detach())
+        if spec.model == "supervised_vae":
+            for i in range(len(spec.input_dims)):
+                block(f"decoders.{i}", res["embedding"].detach())
     return out
 
 
@@ -121,9 +136,9 @@ def grad_keep_mask(name, g, flagged):
     """elements of parameter `name` that are compared strictly (everything except flagged hidden units)"""
     for prefix, units in flagged.items():
         if name.startswith(prefix + ".") and bool(units.any()):
-            if name.endswith("layer_1.weight"):
+            if name.endswith("layer_1.weight") or name.endswith("hidden_layers.0.weight"):
                 return (~units)[:, None].expand_as(g)
-            if name.endswith("batchnorm.weight") or name.endswith("batchnorm.bias"):
+            if name.endswith(("batchnorm.weight", "batchnorm.bias", "hidden_layers.0.bias")):
                 return ~units
     return None
 
@@ -140,6 +155,8 @@ def compare_step(rep, model, spec, batch, cb, st, s, P_before_cpu, lr):
     ws = eng.forward_backward(groups, y, masks)
     for k, v in st["outputs"].items():
         rep.close(f"step{s} outputs[{k}]", ws["heads"]["logits"][k], v)
+    if st.get("embedding") is not None and spec.model == "supervised_vae":
+        rep.close(f"step{s} z", eng.embedding(ws), st["embedding"])
     vals = eng.losses(ws)
     for k, v in st["losses"].items():
         if k == "train_loss":
@@ -162,7 +179,7 @@ def compare_step(rep, model, spec, batch, cb, st, s, P_before_cpu, lr):
 
 
 GOLDEN = [p for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
-          if os.path.basename(p).startswith(("directpred", "triplet"))]
+          if os.path.basename(p).startswith(("directpred", "triplet", "supervised_vae"))]
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
@@ -209,6 +226,7 @@ def oracle_reference(spec, B, lr, steps, seed=0, batch=None):
                        for k in tr.names if P[k] in tr.opt.state}
         res = tr.step(batch, noise)
         out.append(dict(P_before=P_before, adam_before=adam_before, noise=noise.record,
+                        embedding=res["embedding"].detach(),
                         outputs={k: v.detach() for k, v in res["outputs"].items()},
                         losses={**{k: v.detach() for k, v in res["losses"].items()}, "train_loss": res["total"].detach()},
                         grads=res["grads"], grad_norm=res["grad_norm"].detach(),
@@ -229,6 +247,14 @@ CASES = {
     "multitask": (Spec(model="DirectPred", input_dims=[700, 300, 120], latent_dim=48, hidden_dim_factor=0.2,
                        supervisor_hidden_dim=16, variables=["y", "c", "e"], variable_types=VT, num_classes={"c": 7},
                        surv_event_var="e", surv_time_var="t"), 333),
+    # BASELINE.json config 3 architecture (supervised_vae, 2 omics, Cox head, MMD + reconstruction) at reduced size,
+    # ragged widths (h = 61 / 36, batch not a multiple of 128)
+    "svae_cox": (Spec(model="supervised_vae", input_dims=[600, 360], latent_dim=24, hidden_dim_factor=0.1024,
+                      supervisor_hidden_dim=16, variables=["e"], variable_types=VT, surv_event_var="e",
+                      surv_time_var="t"), 300),
+    # latent 128 as in config 3, classification + regression heads, one modality, batch = 512
+    "svae_heads": (Spec(model="supervised_vae", input_dims=[400], latent_dim=128, hidden_dim_factor=0.2,
+                        supervisor_hidden_dim=32, variables=["y", "c"], variable_types=VT, num_classes={"c": 4}), 512),
 }
 
 
