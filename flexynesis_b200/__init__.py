@@ -6,8 +6,8 @@ Importing this package loads flexynesis_b200/lib/libfxn_b200.so (hand-written CU
 include/flexynesis_b200.h); the import fails loudly when the library has not been built.
 """
 from . import _lib  # noqa: F401  (loads the shared library or raises)
-from .models import DirectPred, MultiTripletNetwork, supervised_vae  # noqa: F401
+from .models import DirectPred, GNN, MultiTripletNetwork, supervised_vae  # noqa: F401
 from .data import SyntheticMultiOmicDataset, DeviceBatcher  # noqa: F401
 
-__all__ = ["DirectPred", "MultiTripletNetwork", "supervised_vae", "SyntheticMultiOmicDataset", "DeviceBatcher"]
+__all__ = ["DirectPred", "GNN", "MultiTripletNetwork", "supervised_vae", "SyntheticMultiOmicDataset", "DeviceBatcher"]
 __version__ = "0.1.0"

@@ -85,7 +85,8 @@ SYMBOLS = [
     "fxn_gemm_stat_tiles", "fxn_bn_act_fwd", "fxn_bn_act_bwd", "fxn_col_stats", "fxn_head_out_fwd", "fxn_head_out_bwd",
     "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
-    "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn",
+    "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn", "fxn_gcn_fwd", "fxn_gcn_bwd",
+    "fxn_merge_col_stats",
 ]
 
 
@@ -311,3 +312,23 @@ def loss_weights(n, log_vars, weighting, wts) -> None:
 def randn(out, ld, rows, cols, seed, seed_dev=None) -> None:
     check(lib.fxn_randn(C.c_void_p(out), c_ll(ld), c_ll(rows), C.c_int(cols), C.c_ulonglong(seed), C.c_void_p(seed_dev),
                         C.c_void_p(stream())), "fxn_randn")
+
+
+def gcn_fwd(X, B, N, Fin, rowptr, col, w, W, bias, emb, O, partials) -> None:
+    check(lib.fxn_gcn_fwd(C.c_void_p(X), C.c_int(B), C.c_int(N), C.c_int(Fin), C.c_void_p(rowptr), C.c_void_p(col),
+                          C.c_void_p(w), C.c_void_p(W), C.c_void_p(bias), C.c_int(emb), C.c_void_p(O),
+                          C.c_void_p(partials), C.c_void_p(stream())), "fxn_gcn_fwd")
+
+
+def gcn_bwd(X, dO, B, N, Fin, emb, csr_in, csr_out, W, dW, dbias, dX) -> None:
+    """csr_in / csr_out: (rowptr, col, w) device int32/int32/fp32 tensors (by destination / by source)."""
+    check(lib.fxn_gcn_bwd(C.c_void_p(X), C.c_void_p(dO), C.c_int(B), C.c_int(N), C.c_int(Fin), C.c_int(emb),
+                          C.c_void_p(csr_in[0].data_ptr()), C.c_void_p(csr_in[1].data_ptr()),
+                          C.c_void_p(csr_in[2].data_ptr()), C.c_void_p(csr_out[0].data_ptr()),
+                          C.c_void_p(csr_out[1].data_ptr()), C.c_void_p(csr_out[2].data_ptr()), C.c_void_p(W),
+                          C.c_void_p(dW), C.c_void_p(dbias), C.c_void_p(dX), C.c_void_p(stream())), "fxn_gcn_bwd")
+
+
+def merge_col_stats(partials, ntiles, tile_rows, rows, cols, pld, merged) -> None:
+    check(lib.fxn_merge_col_stats(C.c_void_p(partials), C.c_int(ntiles), C.c_int(tile_rows), c_ll(rows), C.c_int(cols),
+                                  C.c_int(pld), C.c_void_p(merged), C.c_void_p(stream())), "fxn_merge_col_stats")

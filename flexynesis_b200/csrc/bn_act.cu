@@ -51,11 +51,23 @@ struct BnArgs {
   float* out; long long ldo;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ldp;
   float* saved;           // [2][cols]: mean, rstd
+  int rpb;                // rows per block (multiple of 32)
 };
 
 constexpr int BN_COLS = 64;     // columns per block (8 per thread x 8 threads)
 constexpr int BN_ROWS = 64;     // rows per block (2 per thread): many small blocks keep HBM requests in flight
 constexpr int BN_THREADS = 256;
+
+// Rows per block: 64 keeps many small blocks (and HBM requests) in flight for the [4096 x 512]-sized activations of the
+// MLP encoders; tall inputs (flexGCN normalises B*N = 8 M rows of 32 channels) get fatter blocks so that the grid stays
+// within a few waves of 148 SMs and the per-block prologue / column atomics stay negligible.
+static inline int bn_rows_per_block(long long rows, int col_blocks) {
+  const long long target_blocks = 148LL * 16;
+  long long rpb = (rows * col_blocks + target_blocks - 1) / target_blocks;
+  rpb = (rpb + 31) / 32 * 32;
+  if (rpb < BN_ROWS) rpb = BN_ROWS;
+  return static_cast<int>(rpb);
+}
 
 // merge tile partials for one column -> (mean, biased var)
 __device__ __forceinline__ void merge_stats(const float* partials, int ntiles, int tile_rows, long long rows, int cols,
@@ -140,8 +152,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_fwd_kernel(const BnArgs a) {
   const int c = c0 + tc;
   const int pcols = (a.cols + 7) & ~7;             // planes are zero-filled up to pad8(cols) only
   if (c >= pcols || (c >= a.cols && a.out_hi == nullptr)) return;
-  const long long r_begin = static_cast<long long>(blockIdx.y) * BN_ROWS;
-  const long long r_end = min(a.rows, r_begin + BN_ROWS);
+  const long long r_begin = static_cast<long long>(blockIdx.y) * a.rpb;
+  const long long r_end = min(a.rows, r_begin + a.rpb);
   const bool drop = a.train && a.p_drop > 0.f;
   const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
   const bool vec_in = ((reinterpret_cast<uintptr_t>(a.V) & 15) == 0) && (a.ldv % 4 == 0) && (c + 8 <= a.cols);
@@ -216,6 +228,7 @@ struct BnBwdArgs {
   __nv_bfloat16* dv_hi; __nv_bfloat16* dv_lo; long long ldp;
   float grad_scale;                     // multiplies dOut (1 unless the caller folds a loss weight in)
   int acc_affine;                       // dgamma/dbeta += (module applied several times per step)
+  int rpb;                              // rows per block (multiple of 32)
 };
 
 // recompute g = dOut * dropout * act'(y) for 8 columns of row r; also returns xhat
@@ -272,8 +285,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnBwdAr
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  const long long r_begin = static_cast<long long>(blockIdx.y) * BN_ROWS;
-  const long long r_end = min(a.rows, r_begin + BN_ROWS);
+  const long long r_begin = static_cast<long long>(blockIdx.y) * a.rpb;
+  const long long r_end = min(a.rows, r_begin + a.rpb);
   if (c < a.cols) {
     for (long long r = r_begin + tr; r < r_end; r += 32) {
       float g[8], xh[8];
@@ -323,8 +336,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const BnBwdArg
   float sb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sb[j] = 0.f;
-  const long long r_begin = static_cast<long long>(blockIdx.y) * BN_ROWS;
-  const long long r_end = min(a.rows, r_begin + BN_ROWS);
+  const long long r_begin = static_cast<long long>(blockIdx.y) * a.rpb;
+  const long long r_end = min(a.rows, r_begin + a.rpb);
   const int pcols = (a.cols + 7) & ~7;
   if (c < a.cols || (a.dv_hi && c < pcols)) {
     for (long long r = r_begin + tr; r < r_end; r += 32) {
@@ -425,7 +438,8 @@ extern "C" int fxn_bn_act_fwd(const fxn_bn_fwd_desc* d, void* stream_) {
   a.out_hi = static_cast<__nv_bfloat16*>(d->out_hi); a.out_lo = static_cast<__nv_bfloat16*>(d->out_lo); a.ldp = d->ldp;
   a.saved = d->saved;
   const int width = a.out_hi ? ((a.cols + 7) & ~7) : a.cols;
-  dim3 grid(ceil_div(width, BN_COLS), ceil_div(a.rows, BN_ROWS));
+  a.rpb = bn_rows_per_block(a.rows, ceil_div(width, BN_COLS));
+  dim3 grid(ceil_div(width, BN_COLS), ceil_div(a.rows, a.rpb));
   bn_fwd_kernel<<<grid, BN_THREADS, 0, stream>>>(a);
   FXN_CHECK_LAUNCH("bn_fwd");
   return 0;
@@ -449,11 +463,12 @@ extern "C" int fxn_bn_act_bwd(const fxn_bn_bwd_desc* d, void* stream_) {
   cudaError_t e = cudaMemsetAsync(a.sums, 0, sizeof(float) * 2 * a.cols, stream);
   if (e == cudaSuccess && a.dbias) e = cudaMemsetAsync(a.dbias, 0, sizeof(float) * a.cols, stream);
   if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "bn_bwd memset: %s", cudaGetErrorString(e));
-  dim3 grid(ceil_div(a.cols, BN_COLS), ceil_div(a.rows, BN_ROWS));
+  const int width = a.dv_hi ? ((a.cols + 7) & ~7) : a.cols;
+  a.rpb = bn_rows_per_block(a.rows, ceil_div(width, BN_COLS));
+  dim3 grid(ceil_div(a.cols, BN_COLS), ceil_div(a.rows, a.rpb));
   bn_bwd_reduce_kernel<<<grid, BN_THREADS, 0, stream>>>(a);
   FXN_CHECK_LAUNCH("bn_bwd_reduce");
-  const int width = a.dv_hi ? ((a.cols + 7) & ~7) : a.cols;
-  dim3 grid2(ceil_div(width, BN_COLS), ceil_div(a.rows, BN_ROWS));
+  dim3 grid2(ceil_div(width, BN_COLS), ceil_div(a.rows, a.rpb));
   bn_bwd_apply_kernel<<<grid2, BN_THREADS, 0, stream>>>(a);
   FXN_CHECK_LAUNCH("bn_bwd_apply");
   return 0;

@@ -872,3 +872,163 @@ class VAEEngine(EngineBase):
 
     def embedding(self, ws, group: int = 0) -> torch.Tensor:
         return ws["z"][:, :self.latent]
+
+
+# ----------------------------------------------------------------------------------------------------
+# GNN (flexGCN with GCN convolutions)
+# ----------------------------------------------------------------------------------------------------
+def build_gcn_csr(edge_index: torch.Tensor, num_nodes: int, device):
+    """gcn_norm of torch_geometric (add the missing self loops, in-degree on the directed list as given,
+    w = deg_src^-1/2 * deg_dst^-1/2) as two CSRs: by destination (forward / weight gradient) and by source (input
+    gradient). Built once per model; edges of one row keep their edge_index order so sums are reproducible."""
+    ei = edge_index.to("cpu", torch.long)
+    src, dst = ei[0], ei[1]
+    looped = torch.zeros(num_nodes, dtype=torch.bool)
+    looped[src[src == dst]] = True
+    extra = torch.nonzero(~looped).flatten()
+    src, dst = torch.cat([src, extra]), torch.cat([dst, extra])
+    deg = torch.zeros(num_nodes, dtype=torch.float32).scatter_add_(0, dst, torch.ones(dst.numel()))
+    dinv = deg.pow(-0.5)
+    dinv[torch.isinf(dinv)] = 0
+    w = dinv[src] * dinv[dst]
+
+    def csr(key, other):
+        order = torch.sort(key, stable=True).indices
+        counts = torch.bincount(key, minlength=num_nodes)
+        rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64)
+        rowptr[1:] = torch.cumsum(counts, 0)
+        return (rowptr.to(device, torch.int32), other[order].to(device, torch.int32).contiguous(),
+                w[order].to(device, torch.float32).contiguous())
+
+    return csr(dst, src), csr(src, dst)
+
+
+class GNNEngine(EngineBase):
+    """GNN (flexynesis/models/gnn_early.py) with flexGCN(conv='GCN') (modules.py:195-262): num_convs x (GCN aggregate +
+    lin -> BatchNorm1d over B*N rows -> act -> Dropout(0.2)) -> flatten -> fc -> heads."""
+
+    def __init__(self, model, device):
+        super().__init__(model, device)
+        enc = model.encoders[0]
+        self.K = len(enc.convs)
+        self.emb = enc.convs[0].lin.out_features
+        self.F = enc.convs[0].lin.in_features
+        self.N = enc.fc.in_features // self.emb
+        self.p_drop = float(enc.dropout_rate)
+        from .containers import ACTIVATIONS
+        self.act = ACTIVATIONS[enc.act_name]
+        self.wfc = self.wplanes.add_matrix("encoders.0.fc.weight")
+        self.csr_in, self.csr_out = build_gcn_csr(model.edge_index, self.N, self.device)
+        self._finish_init(0)
+
+    def workspace(self, B: int) -> dict:
+        if B in self.ws:
+            return self.ws[B]
+        dev, K, N, emb, Lt, Lp = self.device, self.K, self.N, self.emb, self.latent, self.Lp
+        f = lambda *shape: torch.zeros(*shape, device=dev)
+        ws = dict(B=B)
+        ws["O"] = [f(B * N, emb) for _ in range(K)]
+        ws["D"] = [f(B * N, emb) for _ in range(K - 1)]
+        self.direct_planes = emb % 8 == 0          # the last BatchNorm can write the fc operand planes itself
+        ws["Dlast_p"] = Planes.empty(B, N * emb, dev)
+        ws["Dlast"] = None if self.direct_planes else f(B * N, emb)
+        ws["partials"] = [f(B, 2, emb) for _ in range(K)]
+        ws["merged"] = [f(2, emb) for _ in range(K)]
+        ws["saved"] = [f(2 * emb) for _ in range(K)]
+        ws["sums"] = [f(2 * emb) for _ in range(K)]
+        ws["E"] = f(B, Lp)
+        ws["E_p"] = Planes.empty(B, Lt, dev, ld=Lp)
+        ws["dE_p"] = Planes.empty(B, Lt, dev, ld=Lp)
+        ws["dD"] = f(B * N, emb)
+        ws["dO"] = f(B * N, emb)
+        ws["x"] = None
+        ws["heads"] = self.heads.workspace(B)
+        self.ws[B] = ws
+        return ws
+
+    def _conv_inputs(self, ws):
+        return [ws["x"]] + ws["D"]
+
+    def _forward(self, ws, y, train: bool, masks, with_loss: bool):
+        a, enc, hw = self.arena, self.model.encoders[0], ws["heads"]
+        B, K, N, emb, Lt, Lp = ws["B"], self.K, self.N, self.emb, self.latent, self.Lp
+        rows = B * N
+        hw["acc"].zero_()
+        xin = self._conv_inputs(ws)
+        for k in range(K):
+            fin = self.F if k == 0 else emb
+            L.gcn_fwd(xin[k].data_ptr(), B, N, fin, self.csr_in[0].data_ptr(), self.csr_in[1].data_ptr(),
+                      self.csr_in[2].data_ptr(), a.p(f"encoders.0.convs.{k}.lin.weight"), a.p(f"encoders.0.convs.{k}.bias"),
+                      emb, ws["O"][k].data_ptr(), ws["partials"][k].data_ptr() if train else None)
+            if train:
+                L.merge_col_stats(ws["partials"][k].data_ptr(), B, N, rows, emb, emb, ws["merged"][k].data_ptr())
+            mask = None if masks is None else masks.get(f"encoders.0.dropout.{k}")
+            last = k == K - 1
+            kw = {}
+            if last and self.direct_planes:
+                kw = dict(out_hi=ws["Dlast_p"].hi_ptr, out_lo=ws["Dlast_p"].lo_ptr, ldp=emb)
+            else:
+                dst = ws["Dlast"] if last else ws["D"][k]
+                kw = dict(out=dst.data_ptr(), ldo=emb)
+            L.bn_fwd(V=ws["O"][k].data_ptr(), ldv=emb, rows=rows, cols=emb, partials=ws["merged"][k].data_ptr(), ntiles=1,
+                     tile_rows=rows, gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
+                     momentum=MOMENTUM, eps=EPS, train=int(train), act=self.act, p_drop=self.p_drop if train else 0.0,
+                     mask=None if mask is None else mask.data_ptr(), ldm=emb, seed=self.seed + 7 + 131 * k,
+                     seed_dev=a.step.data_ptr(), saved=ws["saved"][k].data_ptr(), **_bn_ptrs(enc.bns[k]), **kw)
+        if not self.direct_planes:
+            L.split_planes(ws["Dlast"].view(B, N * emb), ws["Dlast_p"])
+        L.gemm(B, Lt, N * emb, ws["Dlast_p"], 0, self.wp(self.wfc), 0, C_ptr=ws["E"].data_ptr(), ldc=Lp,
+               bias=a.p("encoders.0.fc.bias"), splitk=-1)
+        L.split_planes(ws["E"][:, :Lt], ws["E_p"])
+        self.heads.forward(hw, ws["E_p"], B, y, train, masks, with_loss=with_loss)
+        if with_loss:
+            self.heads.total(hw)
+
+    def _stage(self, ws, x: torch.Tensor):
+        x = self._input(x)
+        if x.dim() != 3 or x.shape[1] != self.N or x.shape[2] != self.F:
+            raise ValueError(f"expected node features [B, {self.N}, {self.F}], got {tuple(x.shape)}")
+        ws["x"] = x.contiguous()
+
+    def forward_backward(self, x_groups, y, masks=None):
+        x = x_groups[0][0]
+        B = x.shape[0]
+        ws = self.workspace(B)
+        a, hw = self.arena, ws["heads"]
+        K, N, emb, Lt = self.K, self.N, self.emb, self.latent
+        rows = B * N
+        y = self._labels(y)
+        self.ensure_fresh()
+        self._stage(ws, x)
+        self._forward(ws, y, True, masks, True)
+        # ---- backward ----
+        self.heads.backward(hw, ws["E_p"], B, y, masks, ws["dE_p"], None, a.g("encoders.0.fc.bias"))
+        L.gemm(Lt, N * emb, B, ws["dE_p"], 1, ws["Dlast_p"], 1, C_ptr=a.g("encoders.0.fc.weight"), ldc=N * emb, splitk=-1)
+        L.gemm(B, N * emb, Lt, ws["dE_p"], 0, self.wp(self.wfc), 1, C_ptr=ws["dD"].data_ptr(), ldc=N * emb)
+        xin = self._conv_inputs(ws)
+        for k in reversed(range(K)):
+            fin = self.F if k == 0 else emb
+            mask = None if masks is None else masks.get(f"encoders.0.dropout.{k}")
+            L.bn_bwd(V=ws["O"][k].data_ptr(), ldv=emb, dOut=ws["dD"].data_ptr(), ldg=emb, rows=rows, cols=emb,
+                     gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
+                     saved=ws["saved"][k].data_ptr(), act=self.act, p_drop=self.p_drop,
+                     mask=None if mask is None else mask.data_ptr(), ldm=emb, seed=self.seed + 7 + 131 * k,
+                     seed_dev=a.step.data_ptr(), pre_act=0, sums=ws["sums"][k].data_ptr(),
+                     dgamma=a.g(f"encoders.0.bns.{k}.weight"), dbeta=a.g(f"encoders.0.bns.{k}.bias"),
+                     dV=ws["dO"].data_ptr(), ldd=emb)
+            L.gcn_bwd(xin[k].data_ptr(), ws["dO"].data_ptr(), B, N, fin, emb, self.csr_in, self.csr_out,
+                      a.p(f"encoders.0.convs.{k}.lin.weight"), a.g(f"encoders.0.convs.{k}.lin.weight"),
+                      a.g(f"encoders.0.convs.{k}.bias"), ws["dD"].data_ptr() if k > 0 else None)
+        return ws
+
+    def evaluate(self, x_groups, y=None, train_mode: bool = False, masks=None):
+        x = x_groups[0][0]
+        ws = self.workspace(x.shape[0])
+        self.ensure_fresh()
+        self._stage(ws, x)
+        yl = self._labels(y) if y is not None else None
+        self._forward(ws, yl, train_mode, masks, y is not None)
+        return ws
+
+    def embedding(self, ws, group: int = 0) -> torch.Tensor:
+        return ws["E"][:, :self.latent]

@@ -481,3 +481,99 @@ class supervised_vae(_EngineModel):
         for i in range(steps):
             outs.append(self.forward([x[i] for x in inputs])[4][target_var])
         return torch.cat(outs, dim=0)
+
+
+class GNN(_EngineModel):
+    """Graph-convolutional early-fusion model (flexynesis/models/gnn_early.py:55-140): one flexGCN over node features
+    [B, N, F] with a graph shared by all samples, supervisor heads on its embedding."""
+
+    def __init__(self, config, dataset, target_variables, batch_variables=None, surv_event_var=None,
+                 surv_time_var=None, use_loss_weighting=True, device_type=None, gnn_conv_type=None):
+        super().__init__()
+        self.config = config
+        self.target_variables = target_variables
+        self.surv_event_var, self.surv_time_var = surv_event_var, surv_time_var
+        if surv_event_var is not None and surv_time_var is not None:
+            self.target_variables = self.target_variables + [surv_event_var]
+        self.batch_variables = batch_variables
+        self.variables = self.target_variables + batch_variables if batch_variables else self.target_variables
+        base = getattr(dataset, "multiomic_dataset", dataset)
+        self.variable_types = base.variable_types
+        self.ann = base.ann
+        self.feature_importances = {}
+        self.use_loss_weighting = use_loss_weighting
+        self.device_type = device_type
+        self.gnn_conv_type = gnn_conv_type
+        self.edge_index = dataset.edge_index.to(_resolve_device(device_type))   # shared by all samples: kept on device
+        if use_loss_weighting:
+            self.log_vars = nn.ParameterDict({v: nn.Parameter(torch.zeros(1)) for v in self.variables})
+        first = dataset[0][0]
+        self.encoders = nn.ModuleList([flexGCN(
+            node_count=first.shape[0], node_feature_count=first.shape[1],
+            node_embedding_dim=int(config["node_embedding_dim"]), num_convs=int(config["num_convs"]),
+            output_dim=config["latent_dim"], act=config["activation"], conv=gnn_conv_type)])
+        self.MLPs = nn.ModuleDict()
+        for var in self.variables:
+            classes = 1 if self.variable_types[var] == "numerical" else len(np.unique(self.ann[var]))
+            self.MLPs[var] = MLP(config["latent_dim"], config["supervisor_hidden_dim"], classes)
+
+    def _make_engine(self, device):
+        from .engine import GNNEngine
+        return GNNEngine(self, device)
+
+    def _split_batch(self, batch):
+        return [[batch[0]]], batch[1]
+
+    def _same_graph(self, edge_index) -> bool:
+        return edge_index is None or edge_index is self.edge_index or (
+            edge_index.shape == self.edge_index.shape and bool((edge_index.to(self.edge_index.device) == self.edge_index).all()))
+
+    def _embed(self, x, edge_index=None):
+        """flexGCN embedding [B, latent]; engine for CUDA inputs on the model's own graph, torch containers otherwise."""
+        use_engine = x.is_cuda and not x.requires_grad and not (self.training and torch.is_grad_enabled()) \
+            and self._same_graph(edge_index)
+        if use_engine:
+            eng = self.engine(x.device)
+            ws = eng.evaluate([[x]], None, train_mode=self.training)
+            return eng.embedding(ws).clone(), self._outputs_from_ws(eng, ws)
+        ei = self.edge_index if edge_index is None else edge_index
+        emb = self.encoders[0](x, ei.to(x.device))
+        return emb, {v: mlp(emb) for v, mlp in self.MLPs.items()}
+
+    def forward(self, x, edge_index=None):
+        return self._embed(x, edge_index)[1]
+
+    def _node_batches(self, dataset, batch_size):
+        n = len(dataset)
+        feats = getattr(dataset, "node_features_tensor", None)
+        for s in range(0, n, batch_size):
+            idx = range(s, min(s + batch_size, n))
+            x = feats[s:s + batch_size] if feats is not None else torch.stack([dataset[i][0] for i in idx])
+            yield x, [dataset[i][2] for i in idx] if feats is None else list(dataset.samples[s:s + batch_size])
+
+    def _run_eval(self, dataset, want):
+        self.eval()
+        device = _resolve_device(self.device_type)
+        self.to(device)
+        self.edge_index = self.edge_index.to(device)
+        vt = getattr(dataset, "variable_types", self.variable_types)
+        out = {v: [] for v in self.variables}
+        embs, names = [], []
+        with torch.no_grad():
+            for x, samples in self._node_batches(dataset, 4096 if device.type == "cuda" else 64):
+                emb, outputs = self._embed(x.to(device, torch.float32), dataset.edge_index.to(device))
+                embs.append(emb.detach().cpu())
+                names.extend(samples)
+                for v in self.variables:
+                    o = outputs[v].detach().float().cpu()
+                    out[v].append(torch.softmax(o, dim=1) if vt[v] == "categorical" else o)
+        if want == "embedding":
+            e = torch.cat(embs, 0)
+            return pd.DataFrame(e.numpy(), index=names, columns=[f"E{i}" for i in range(e.shape[1])])
+        return {v: torch.cat(p).numpy() for v, p in out.items()}
+
+    def predict(self, dataset):
+        return self._run_eval(dataset, "predict")
+
+    def transform(self, dataset):
+        return self._run_eval(dataset, "embedding")

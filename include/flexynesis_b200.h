@@ -192,6 +192,24 @@ int fxn_mmd_grad(const float* z, long long ldz, const float* cs_zz, const float*
  * forward pass (they depend on parameters only). */
 int fxn_loss_weights(int n, const float* const* log_vars, int weighting, float* wts, void* stream);
 
+/* ---- GCN layer of flexGCN (flexynesis/modules.py:252-257; torch_geometric.nn.GCNConv as called at :221-226, :254) ----
+ * Batched dense node features X [B, N, Fin] (contiguous fp32), one shared graph given as CSR by DESTINATION node:
+ * rowptr[N+1], col[nnz] = source node of each in-edge, w[nnz] = symmetric-normalised weight deg_u^-1/2 deg_v^-1/2 with the
+ * missing self loops added (gcn_norm). O[b, v, :] = W * (sum_e w_e X[b, col_e, :]) + bias, W [emb x Fin] = lin.weight.
+ * partials (optional) [B][2][emb]: per-sample column statistics (sum, M2 about the sample mean) of O for the
+ * BatchNorm1d over B*N rows that follows. Fin, emb <= 32. */
+int fxn_gcn_fwd(const float* X, int B, int N, int Fin, const int* rowptr, const int* col, const float* w, const float* W,
+                const float* bias, int emb, float* O, float* partials, void* stream);
+/* Backward: dW [emb x Fin] and dbias [emb] (zeroed by the call), and, when dX != NULL, dX [B, N, Fin] through the
+ * transposed graph (CSR by SOURCE node: rowptr_out, col_out = destination of each out-edge, w_out). */
+int fxn_gcn_bwd(const float* X, const float* dO, int B, int N, int Fin, int emb, const int* rowptr_in, const int* col_in,
+                const float* w_in, const int* rowptr_out, const int* col_out, const float* w_out, const float* W,
+                float* dW, float* dbias, float* dX, void* stream);
+/* Chan-merge [ntiles][2][pld] column partials (tile_rows rows per tile) into one record merged[2][cols] = (sum, M2),
+ * which fxn_bn_act_fwd accepts as partials with ntiles = 1, tile_rows = rows. */
+int fxn_merge_col_stats(const float* partials, int ntiles, int tile_rows, long long rows, int cols, int pld,
+                        float* merged, void* stream);
+
 /* ---- step policy ----
  * clip_grad_norm_(params, max_norm) + Adam on flat arenas (flexynesis/main.py:216-217, direct_pred.py:135-144).
  * grads are multiplied by grad_scale (1/world_size after a sum all-reduce) before the norm. *step_counter (int64)

@@ -37,11 +37,34 @@ def _close(tag, got, ref, rtol=RTOL, atol=1e-6):
     assert err <= atol + rtol * scale, f"{tag}: abs err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e})"
 
 
-def build_model(spec: Spec, batch, lr, P0=None):
+class _GDS:
+    """MultiOmicDatasetNW duck type: node features [B, N, F], labels, one shared edge_index"""
+
+    def __init__(self, x, ann, variable_types, edge_index):
+        self.node_features_tensor, self.edge_index, self.variable_types = x, edge_index, variable_types
+        self.ann = {k: torch.nan_to_num(v, nan=0.0) for k, v in ann.items()}
+        self.samples = [f"s{i}" for i in range(x.shape[0])]
+
+    def __getitem__(self, i):
+        return self.node_features_tensor[i], {k: v[i] for k, v in self.ann.items()}, self.samples[i]
+
+    def __len__(self):
+        return len(self.samples)
+
+
+def build_model(spec: Spec, batch, lr, P0=None, edge_index=None):
     import flexynesis_b200 as fx
     cfg = {"latent_dim": spec.latent_dim, "hidden_dim_factor": spec.hidden_dim_factor,
-           "supervisor_hidden_dim": spec.supervisor_hidden_dim, "lr": lr}
+           "supervisor_hidden_dim": spec.supervisor_hidden_dim, "lr": lr,
+           "node_embedding_dim": spec.node_embedding_dim, "num_convs": spec.num_convs, "activation": spec.activation}
     targets = [v for v in spec.variables if v != spec.surv_event_var]
+    if spec.model == "GNN":
+        ds = _GDS(batch[0], batch[1], spec.variable_types, edge_index)
+        model = fx.GNN(cfg, ds, targets, surv_event_var=spec.surv_event_var, surv_time_var=spec.surv_time_var,
+                       use_loss_weighting=spec.use_loss_weighting, device_type="gpu", gnn_conv_type="GCN")
+        if P0 is not None:
+            model.load_state_dict(P0, strict=True)
+        return model.cuda()
     if spec.model == "MultiTripletNetwork":
         ds = _DS(batch[0], batch[3], spec.variable_types)
         cls = fx.MultiTripletNetwork
@@ -121,7 +144,7 @@ def gate_margin_units(spec, P, batch, res, masks, margin=2e-4):
             for d in batch[:3]:
                 for i, x in enumerate(d.values()):
                     block(f"encoders.{i}", x)
-        else:
+        elif spec.model != "GNN":
             for i, x in enumerate(batch[0].values()):
                 block(f"encoders.{i}", x)
         for v in spec.variables:
@@ -179,7 +202,7 @@ def compare_step(rep, model, spec, batch, cb, st, s, P_before_cpu, lr):
 
 
 GOLDEN = [p for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
-          if os.path.basename(p).startswith(("directpred", "triplet", "supervised_vae"))]
+          if os.path.basename(p).startswith(("directpred", "triplet", "supervised_vae", "gnn"))]
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
@@ -188,7 +211,13 @@ def test_engine_matches_reference_golden(path):
     g = torch.load(path, weights_only=False)
     spec = Spec(**g["spec"])
     rep = Report()
-    model = build_model(spec, g["batch"], g["lr"], g["P0"])
+    model = build_model(spec, g["batch"], g["lr"], g["P0"], g.get("edge_index"))
+    if g["eval_outputs0"] is not None and spec.model == "GNN":
+        model.eval()
+        with torch.no_grad():
+            out = model.forward(g["batch"][0].cuda())
+        for k, v in g["eval_outputs0"].items():
+            rep.close(f"initial eval outputs[{k}]", out[k], v)
     if g["eval_outputs0"] is not None and spec.model == "DirectPred":
         model.eval()
         with torch.no_grad():
@@ -201,13 +230,13 @@ def test_engine_matches_reference_golden(path):
         sync_state(model, st["P_before"])
         # flag near-zero ReLU gates with the oracle forward at this state
         P = {k: v.clone() for k, v in st["P_before"].items()}
-        res = forward(P, spec, g["batch"], True, Noise(st["noise"]))
+        res = forward(P, spec, g["batch"], True, Noise(st["noise"]), g.get("edge_index"))
         st["flagged"] = gate_margin_units(spec, st["P_before"], g["batch"], res, None)
         compare_step(rep, model, spec, g["batch"], cb, st, s, st["P_before"], g["lr"])
     rep.finish()
 
 
-def oracle_reference(spec, B, lr, steps, seed=0, batch=None):
+def oracle_reference(spec, B, lr, steps, seed=0, batch=None, edge_index=None):
     """Run the CPU oracle for `steps` steps; records pre-step state, noise, results and Adam moments."""
     torch.manual_seed(seed)
     from oracle.restatement import init_params
@@ -216,7 +245,10 @@ def oracle_reference(spec, B, lr, steps, seed=0, batch=None):
     if batch is None:
         dat, y = synthetic_batch(spec, B, seed)
         batch = (dat, y, None)
-    tr = Trainer(P, spec, lr)
+        if spec.model == "GNN":
+            g = torch.Generator().manual_seed(seed + 1)
+            batch = (torch.randn(B, spec.node_count, spec.input_dims[0], generator=g), y, None)
+    tr = Trainer(P, spec, lr, edge_index=edge_index)
     out = []
     for s in range(steps):
         torch.manual_seed(1000 + s)
@@ -291,6 +323,35 @@ def test_engine_matches_oracle(name):
                 rep.close(f"step{s} untouched {k}", sd[k], st["P_before"][k], rtol=0, atol=0)
             else:
                 rep.close(f"step{s} adam {k}", sd[k], st["P_after"][k], rtol=2e-6, atol=2e-7)
+    rep.finish()
+
+
+GNN_CASES = {
+    # BASELINE.json config 4 architecture (1 feature per node, GCN 1 -> 32 -> 32, fc N*32 -> 128) at reduced size
+    "cfg4_small": (Spec(model="GNN", input_dims=[1], latent_dim=128, supervisor_hidden_dim=32, variables=["y"],
+                        variable_types=VT, node_count=300, node_embedding_dim=32, num_convs=2, activation="relu"), 96, 3000),
+    # ragged: 3 features per node, embedding 12 (not a multiple of 8), 3 convolutions, two heads, nodes without in-edges
+    "ragged": (Spec(model="GNN", input_dims=[3], latent_dim=20, supervisor_hidden_dim=8, variables=["y", "c"],
+                    variable_types=VT, num_classes={"c": 3}, node_count=77, node_embedding_dim=12, num_convs=3,
+                    activation="relu"), 50, 120),
+}
+
+
+@pytest.mark.parametrize("name", list(GNN_CASES))
+def test_gnn_matches_oracle(name):
+    from oracle.restatement import synthetic_graph
+    spec, B, n_edges = GNN_CASES[name]
+    lr = 1e-3
+    edge_index = synthetic_graph(spec.node_count, n_edges, 0)
+    P0, batch, steps, _ = oracle_reference(spec, B, lr, steps=2, edge_index=edge_index)
+    model = build_model(spec, batch, lr, P0, edge_index)
+    model.train()
+    cb = to_cuda(batch)
+    rep = Report()
+    for s, st in enumerate(steps):
+        sync_state(model, st["P_before"])
+        st["flagged"] = {}
+        compare_step(rep, model, spec, batch, cb, st, s, st["P_before"], lr)
     rep.finish()
 
 
