@@ -1,16 +1,17 @@
 #!/usr/bin/env python
-"""Benchmark of the flexynesis training hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+"""Benchmark of the flexynesis training hot path on B200 (contract: task statement / DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg1|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg1|cfg3|cfg4|cfg5]
 
 Metric (BASELINE.json): training samples/sec of DirectPred, 2 omics (4096 x 5000 + 4096 x 3000), intermediate fusion,
 encoder hidden = int(0.1024 d) -> latent 256, supervisor hidden 32, one 5-class target, full-batch steps of 4096
-(SURVEY.md section 8 "cfg 2"). A step = forward + backward + clip_grad_norm_(1.0) + Adam over one batch.
+(SURVEY.md section 8 "cfg 2"; the default workload). A step = forward + backward + clip_grad_norm_(1.0) + Adam over
+one batch. The other BASELINE.json configs are selectable with --workload (cfg5 = the per-GPU shard of config 5).
 
   value        whole-job samples/s, batch already resident in HBM, CUDA-event timed, max over ranks
-  e2e          same metric through the public API (model.fit_step) with the batch copied from pinned host memory every
-               step and the loss read back every step
-  roofline     the dominant kernel (tcgen05 GEMM of encoder 0's first Linear) timed alone with CUDA events
+  e2e          same metric through the public API with the batch copied from pinned host memory every step and the
+               loss read back every step
+  roofline     the dominant kernel timed alone with CUDA events (L2 flushed between launches)
   cpu_baseline the oracle port of the reference's CPU path timed on this box's host cores (rank 0, N = 1)
   --impl reference   times that CPU path alone, with all host threads, on the same config
 """
@@ -29,39 +30,132 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+VT = {"y": "numerical", "c": "categorical", "e": "numerical", "t": "numerical"}
 WORKLOADS = {
-    # name: (input_dims, batch, latent, hidden_dim_factor, supervisor_hidden, variables)
-    "cfg1": dict(dims=[1000], B=512, latent=64, hdf=0.128, sh=32, vars={"y": "numerical"}, classes={}),
-    "cfg2": dict(dims=[5000, 3000], B=4096, latent=256, hdf=0.1024, sh=32, vars={"c": "categorical"}, classes={"c": 5}),
-    "cfg5": dict(dims=[24000], B=4096, latent=512, hdf=0.04267, sh=256, vars={"y": "numerical", "c": "categorical"},
-                 classes={"c": 5}),
-}
-DESCRIBE = {
-    "cfg1": "DirectPred 1 omics 512x1000 -> 128 -> 64, 1 regression target",
-    "cfg2": "DirectPred 2 omics 4096x5000+4096x3000, intermediate fusion, hidden [512,307] -> 256, 5-class head",
-    "cfg5": "DirectPred early fusion 4096x24000 per GPU -> 1024 -> 512, regression + 5-class heads",
+    "cfg1": dict(model="DirectPred", dims=[1000], B=512, latent=64, hdf=0.128, sh=32, vars=["y"], classes={},
+                 describe="DirectPred 1 omics 512x1000 -> 128 -> 64, 1 regression target"),
+    "cfg2": dict(model="DirectPred", dims=[5000, 3000], B=4096, latent=256, hdf=0.1024, sh=32, vars=["c"], classes={"c": 5},
+                 describe="DirectPred 2 omics 4096x5000+4096x3000, intermediate fusion, hidden [512,307] -> 256, "
+                          "5-class head"),
+    "cfg3": dict(model="supervised_vae", dims=[5000, 3000], B=4096, latent=128, hdf=0.1024, sh=32, vars=["e"], classes={},
+                 surv=("e", "t"),
+                 describe="supervised_vae 2 omics 4096x5000+4096x3000, hidden [512,307], latent 128, MMD + reconstruction "
+                          "+ Cox head"),
+    "cfg4": dict(model="GNN", dims=[1], B=4096, latent=128, hdf=0.0, sh=32, vars=["y"], classes={}, nodes=2000, edges=20000,
+                 emb=32, convs=2,
+                 describe="GNN 4096 x 2000 nodes x 1 feature, 20000-edge graph, 2 x GCN(32) + BN, fc 64000 -> 128, "
+                          "1 regression target"),
+    "cfg5": dict(model="DirectPred", dims=[24000], B=4096, latent=512, hdf=0.04267, sh=256, vars=["y", "c"],
+                 classes={"c": 5},
+                 describe="DirectPred early fusion 4096x24000 per GPU -> 1024 -> 512, regression + 5-class heads"),
 }
 
 
 def train_flops_per_sample(w) -> float:
     """Algorithmic training FLOPs per sample: 2*MACs, fwd + dgrad + wgrad, no dgrad for the
-    input layer."""
-    dims, L, sh = w["dims"], w["latent"], w["sh"]
+    input layer; norm / activation / loss / optimizer FLOPs excluded."""
+    L, sh = w["latent"], w["sh"]
+    heads = 0
+    for v in w["vars"]:
+        heads += L * sh + sh * (w["classes"].get(v, 1))
+    if w["model"] == "GNN":
+        n, emb = w["nodes"], w["emb"]
+        lin = n * (w["dims"][0] * emb + (w["convs"] - 1) * emb * emb)
+        fc = n * emb * L
+        return 2.0 * 3.0 * (lin + fc + heads)
+    dims = w["dims"]
     h = [max(int(d * w["hdf"]), 2) for d in dims]
     n = len(dims)
     first = sum(d * hh for d, hh in zip(dims, h))
-    rest = sum(hh * L for hh in h) + (n * L * L if n > 1 else 0)
-    for v, kind in w["vars"].items():
-        c = 1 if kind == "numerical" else w["classes"][v]
-        rest += L * sh + sh * c
+    if w["model"] == "supervised_vae":
+        rest = 2 * sum(hh * L for hh in h) + 2 * n * L * L + sum(L * hh for hh in h) + heads
+        dec_out = sum(d * hh for d, hh in zip(dims, h))
+        gram = w["B"] * L * 2                      # K(z,z) and K(z,z) Z, per sample
+        return 2.0 * (2.0 * first + 3.0 * (rest + dec_out) + gram)
+    rest = sum(hh * L for hh in h) + (n * L * L if n > 1 else 0) + heads
     return 2.0 * (2.0 * first + 3.0 * rest)
 
 
 def make_spec(w):
     from oracle.restatement import Spec
-    return Spec(model="DirectPred", input_dims=list(w["dims"]), latent_dim=w["latent"], hidden_dim_factor=w["hdf"],
-                supervisor_hidden_dim=w["sh"], variables=list(w["vars"]), variable_types=dict(w["vars"]),
-                num_classes=dict(w["classes"]))
+    surv = w.get("surv", (None, None))
+    return Spec(model=w["model"], input_dims=list(w["dims"]), latent_dim=w["latent"], hidden_dim_factor=w["hdf"],
+                supervisor_hidden_dim=w["sh"], variables=list(w["vars"]), variable_types=dict(VT),
+                num_classes=dict(w["classes"]), surv_event_var=surv[0], surv_time_var=surv[1],
+                node_count=w.get("nodes", 0), node_embedding_dim=w.get("emb", 0), num_convs=w.get("convs", 2))
+
+
+def synthetic_graph_fast(num_nodes: int, num_edges: int, seed: int = 0) -> torch.Tensor:
+    """`num_edges` distinct unordered node pairs, random orientation, each stored once."""
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randint(0, num_nodes, (num_edges * 3,), generator=g)
+    b = torch.randint(0, num_nodes, (num_edges * 3,), generator=g)
+    keep = a != b
+    a, b = a[keep], b[keep]
+    uniq = torch.unique(torch.minimum(a, b) * num_nodes + torch.maximum(a, b))
+    uniq = uniq[torch.randperm(uniq.numel(), generator=g)[:num_edges]]
+    lo, hi = uniq // num_nodes, uniq % num_nodes
+    flip = torch.rand(uniq.numel(), generator=g) < 0.5
+    return torch.stack([torch.where(flip, hi, lo), torch.where(flip, lo, hi)]).long()
+
+
+class _View:
+    """constructor view of a dataset (np.unique must not count NaN as a class)"""
+
+
+class _GraphView(_View):
+    """MultiOmicDatasetNW duck type"""
+
+    def __getitem__(self, i):
+        return self.node_features_tensor[i], {}, self.samples[i]
+
+    def __len__(self):
+        return len(self.samples)
+
+
+def build_problem(w, rank: int = 0):
+    """(host dataset pieces, constructor view) for one rank's shard: synthetic matrices of SURVEY.md section 8d."""
+    import flexynesis_b200 as fx
+    B = w["B"]
+    surv = w.get("surv", (None, None))
+    vt = {v: VT[v] for v in w["vars"]}
+    if surv[1]:
+        vt[surv[1]] = "numerical"
+    if w["model"] == "GNN":
+        g = torch.Generator().manual_seed(1000 + rank)
+        ds = fx.SyntheticMultiOmicDataset([8], B, vt, w["classes"], seed=rank)
+        x = torch.randn(B, w["nodes"], w["dims"][0], generator=g)
+        view = _GraphView()
+        view.node_features_tensor, view.edge_index = x, synthetic_graph_fast(w["nodes"], w["edges"], 0)
+        view.variable_types, view.ann, view.samples = ds.variable_types, ds.clean_ann(), ds.samples
+        return dict(x=x, ann=ds.ann, view=view, kind="graph")
+    ds = fx.SyntheticMultiOmicDataset(w["dims"], B, vt, w["classes"], surv_event_var=surv[0], surv_time_var=surv[1],
+                                      seed=rank)
+    view = _View()
+    view.dat, view.features, view.variable_types, view.ann = ds.dat, ds.features, ds.variable_types, ds.clean_ann()
+    return dict(dat=ds.dat, ann=ds.ann, view=view, kind="omics")
+
+
+def build_model(w, prob, dev):
+    import flexynesis_b200 as fx
+    cfg = {"latent_dim": w["latent"], "hidden_dim_factor": w["hdf"], "supervisor_hidden_dim": w["sh"], "lr": 1e-3,
+           "node_embedding_dim": w.get("emb", 0), "num_convs": w.get("convs", 2), "activation": "relu"}
+    surv = w.get("surv", (None, None))
+    targets = [v for v in w["vars"] if v != surv[0]]
+    torch.manual_seed(0)
+    kw = dict(surv_event_var=surv[0], surv_time_var=surv[1], device_type="gpu")
+    if w["model"] == "GNN":
+        model = fx.GNN(cfg, prob["view"], targets, gnn_conv_type="GCN", **kw)
+    else:
+        model = getattr(fx, w["model"])(cfg, prob["view"], targets, **kw)
+    return model.to(dev).train()
+
+
+def device_batch(prob, dev):
+    ann = {k: v.to(dev) for k, v in prob["ann"].items()}
+    if prob["kind"] == "graph":
+        return (prob["x"].to(dev), ann, None)
+    return ({k: v.to(dev) for k, v in prob["dat"].items()}, ann, None)
 
 
 class ClockSampler:
@@ -76,7 +170,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -110,23 +204,45 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm)}
 
 
-def cpu_reference_steps(w, steps, warmup, threads):
-    """The reference's CPU training step (oracle port: same torch ops as flexynesis/modules.py + models/direct_pred.py
-    + Lightning's clip/Adam policy) on a pre-collated batch, all host threads."""
+def cpu_model_name() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_reference_steps(w, steps, warmup, threads, budget_s: float = 60.0):
+    """The reference's CPU training step (oracle port: same torch ops as flexynesis/modules.py + models/*.py +
+    Lightning's clip/Adam policy) on a pre-collated batch with all host threads. Stops early once `budget_s` of timed
+    work has been done (bounded sample)."""
     from oracle.restatement import Trainer, init_params, synthetic_batch
     torch.set_num_threads(threads)
     spec = make_spec(w)
     torch.manual_seed(0)
     P = init_params(spec)
     dat, y = synthetic_batch(spec, w["B"], 0)
-    tr = Trainer(P, spec, 1e-3)
+    edge_index = None
+    if w["model"] == "GNN":
+        g = torch.Generator().manual_seed(1)
+        batch = (torch.randn(w["B"], w["nodes"], w["dims"][0], generator=g), y, None)
+        edge_index = synthetic_graph_fast(w["nodes"], w["edges"], 0)
+    else:
+        batch = (dat, y, None)
+    tr = Trainer(P, spec, 1e-3, edge_index=edge_index)
     for _ in range(warmup):
-        tr.step((dat, y, None))
+        tr.step(batch)
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
-        tr.step((dat, y, None))
+        tr.step(batch)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
-    return w["B"] * steps / dt, dt / steps
+    return w["B"] * done / dt, dt / done, done
 
 
 def run_reference(args, w):
@@ -134,25 +250,116 @@ def run_reference(args, w):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sps, per_step = cpu_reference_steps(w, args.steps, args.warmup, threads)
+    sps, per_step, done = cpu_reference_steps(w, args.steps, min(args.warmup, 3), threads, budget_s=120.0)
     line = {
         "impl": "reference", "metric": "train_samples_per_sec", "value": sps, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 3), "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": DESCRIBE[args.workload], "batch": w["B"], "name": args.workload},
-        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} full-batch steps (B={w['B']}) after {args.warmup} warm-up, pre-collated batch; "
-                                   "oracle port of the reference's torch CPU path (real Lightning is not installable offline)"},
+        "config": {"workload": w["describe"], "batch": w["B"], "name": args.workload},
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "cpu": cpu_model_name(),
+                         "sample": f"{done} full-batch steps (B={w['B']}) after warm-up, pre-collated batch; oracle port "
+                                   "of the reference's torch CPU path (real Lightning is not installable offline)"},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def measured_traffic(workload: str):
+    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture (profiles/traffic.json),
+    or None when no capture of this workload has been taken."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(workload)
+    except Exception:
+        return None
+
+
+def roofline_gemm(model, w, dev):
+    """Encoder-0 first-layer GEMM (the largest contraction of the step) timed alone, L2 flushed between launches."""
+    from flexynesis_b200 import _lib as L
+    eng = model.engine()
+    B = w["B"]
+    ws = eng.ws[B]
+    M, N, K = B, eng.h[0], eng.d[0]
+    if w["model"] == "supervised_vae":
+        out, bias, epi = ws["A"][0], eng.arena.p("encoders.0.hidden_layers.0.bias"), 6
+    else:
+        out, bias, epi = ws["Z"][0], eng.arena.p("encoders.0.layer_1.bias"), 0
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    evs = []
+    for _ in range(13):
+        flush.zero_()                                   # > L2: the next launch reads its operands from HBM
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        L.gemm(M, N, K, ws["X"][0], 0, eng.wp(eng.w1[0]), 0, C_ptr=out.data_ptr(), ldc=out.stride(0), bias=bias,
+               epi_act=epi, colstats=ws["partials"][0].data_ptr(), stats_mode=2)
+        a1.record()
+        evs.append((a0, a1))
+    torch.cuda.synchronize()
+    durs = sorted(a.elapsed_time(b) for a, b in evs[3:])
+    avg_ms = sum(durs) / len(durs)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    achieved = 2.0 * M * N * K / (avg_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": f"gemm_umma_kernel (encoder 0 first Linear [{M}x{K}]x[{K}x{N}], fused bias + BN "
+                                         "column stats)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone), of measured" if peaks
+            else "1590 TFLOP/s, of fallback",
+            "issued_tflops": 3 * achieved, "issued_frac": 3 * achieved / peak,
+            "note": "fp32-grade GEMM = 3 bf16 tcgen05 MMAs per algorithmic MAC (hi*hi + hi*lo + lo*hi); frac is "
+                    "algorithmic, issued_frac is what the tensor pipe executes",
+            "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes": 4.0 * (M * K + N * K + M * N),
+            "traffic": measured_traffic(w.get("name", ""))}
+
+
+def roofline_gcn(model, w, dev):
+    """Second GCN layer forward (reads [B,N,32], writes [B,N,32]) timed alone: HBM-bound."""
+    from flexynesis_b200 import _lib as L
+    eng = model.engine()
+    B = w["B"]
+    ws = eng.ws[B]
+    N, emb = eng.N, eng.emb
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    evs = []
+    k = eng.K - 1
+    xin = eng._conv_inputs(ws)[k]
+    fin = eng.F if k == 0 else emb
+    for _ in range(9):
+        flush.zero_()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        L.gcn_fwd(xin.data_ptr(), B, N, fin, eng.csr_in[0].data_ptr(), eng.csr_in[1].data_ptr(), eng.csr_in[2].data_ptr(),
+                  eng.arena.p(f"encoders.0.convs.{k}.lin.weight"), eng.arena.p(f"encoders.0.convs.{k}.bias"), emb,
+                  ws["O"][k].data_ptr(), ws["partials"][k].data_ptr())
+        a1.record()
+        evs.append((a0, a1))
+    torch.cuda.synchronize()
+    durs = sorted(a.elapsed_time(b) for a, b in evs[2:])
+    avg_ms = sum(durs) / len(durs)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    nbytes = 4.0 * B * N * (fin + emb)
+    achieved = nbytes / (avg_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": f"gcn_fwd_kernel (GCN layer {k}: gather-aggregate + lin, [B,N,{fin}] -> [B,N,{emb}])",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs, of measured" if peaks else "6650 GB/s, of fallback",
+            "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes": nbytes, "traffic": measured_traffic(w.get("name", ""))}
+
+
 def run_b200(args, w):
     import torch.distributed as dist
-    import flexynesis_b200 as fx
     from flexynesis_b200 import _lib as L
     from flexynesis_b200.fit import GraphedStep
+    from flexynesis_b200.parallel import GradAllReduce
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -162,29 +369,16 @@ def run_b200(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = w["B"]
-    vt = dict(w["vars"])
-    ds = fx.SyntheticMultiOmicDataset(w["dims"], B, vt, w["classes"], seed=rank)       # this rank's shard
-    cfg = {"latent_dim": w["latent"], "hidden_dim_factor": w["hdf"], "supervisor_hidden_dim": w["sh"], "lr": 1e-3}
-
-    class CtorView:   # np.unique must not count NaN as a class
-        pass
-    cv = CtorView()
-    cv.dat, cv.features, cv.variable_types, cv.ann = ds.dat, ds.features, ds.variable_types, ds.clean_ann()
-    torch.manual_seed(0)
-    model = fx.DirectPred(cfg, cv, list(w["vars"]), device_type="gpu").to(dev)
-    model.train()
+    prob = build_problem(w, rank)                      # this rank's shard of the sample-sharded dataset
+    model = build_model(w, prob, dev)
     nparams = sum(p.numel() for p in model.parameters())
 
     # ---------------- resident-input arm (value) ----------------
-    dat_dev = {k: v.to(dev) for k, v in ds.dat.items()}
-    ann_dev = {k: v.to(dev) for k, v in ds.ann.items()}
-    batch = (dat_dev, ann_dev, None)
-    allreduce = None
-    if world > 1:
-        def allreduce(flat):
-            dist.all_reduce(flat)
+    batch = device_batch(prob, dev)
+    allreduce = GradAllReduce(world) if world > 1 else None
     step = GraphedStep(model, batch, allreduce=allreduce, grad_scale=1.0 / world)
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -215,20 +409,21 @@ def run_b200(args, w):
             print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "launches_per_step": step.launches_per_step}))
         return
     # ---------------- end-to-end arm (host batch -> device every step, loss read back every step) ----------------
-    host = {k: v.pin_memory() for k, v in ds.dat.items()}
-    host_y = {k: v.pin_memory() for k, v in ds.ann.items()}
-    sx = {k: torch.empty_like(v, device=dev) for k, v in ds.dat.items()}
-    sy = {k: torch.empty_like(v, device=dev) for k, v in ds.ann.items()}
-    for k in sx:
-        sx[k].copy_(host[k])
+    host_x = [v.pin_memory() for v in ([prob["x"]] if prob["kind"] == "graph" else prob["dat"].values())]
+    host_y = {k: v.pin_memory() for k, v in prob["ann"].items()}
+    sx = [torch.empty_like(v, device=dev) for v in host_x]
+    sy = {k: torch.empty_like(v, device=dev) for k, v in host_y.items()}
+    for d, s in zip(sx, host_x):
+        d.copy_(s)
     for k in sy:
         sy[k].copy_(host_y[k])
-    e2e_step = GraphedStep(model, (sx, sy, None), resplit_inputs=True, allreduce=allreduce, grad_scale=1.0 / world)
-    h2d = sum(v.numel() * 4 for v in host.values()) + sum(v.numel() * 4 for v in host_y.values())
+    ebatch = (sx[0], sy, None) if prob["kind"] == "graph" else (dict(zip(prob["dat"].keys(), sx)), sy, None)
+    e2e_step = GraphedStep(model, ebatch, resplit_inputs=True, allreduce=allreduce, grad_scale=1.0 / world)
+    h2d = sum(v.numel() * 4 for v in host_x) + sum(v.numel() * 4 for v in host_y.values())
 
     def e2e_once():
-        for k in sx:
-            sx[k].copy_(host[k], non_blocking=True)
+        for d, s in zip(sx, host_x):
+            d.copy_(s, non_blocking=True)
         for k in sy:
             sy[k].copy_(host_y[k], non_blocking=True)
         e2e_step()
@@ -249,61 +444,31 @@ def run_b200(args, w):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(dt)
 
-    # ---------------- roofline of the dominant kernel (rank 0) ----------------
-    roofline = None
-    cpu_base = None
+    # ---------------- roofline of the dominant kernel + CPU baseline (rank 0) ----------------
+    roofline = cpu_base = None
     if rank == 0:
-        eng = model.engine()
-        ws = eng.ws[B]
-        i = 0
-        M, N, K = B, eng.h[i], eng.d[i]
-        flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-        evs = []
-        zbuf = ws["Z"][i]
-        for it in range(13):
-            flush.zero_()                                   # > L2: the next launch reads its operands from HBM
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            L.gemm(M, N, K, ws["X"][i], 0, eng.wp(eng.w1[i]), 0, C_ptr=zbuf.data_ptr(), ldc=zbuf.stride(0),
-                   bias=eng.arena.p(f"encoders.{i}.layer_1.bias"), colstats=ws["partials"][i].data_ptr(), stats_mode=2)
-            a1.record()
-            evs.append((a0, a1))
-        torch.cuda.synchronize()
-        durs = sorted(a.elapsed_time(b) for a, b in evs[3:])
-        avg_ms = sum(durs) / len(durs)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("bf16_tflops", 1590.0))
-        achieved = 2.0 * M * N * K / (avg_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "gemm_umma_kernel (encoder 0 layer_1 forward, fused bias + BN column stats)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590",
-                    "issued_tflops": 3 * achieved, "issued_frac": 3 * achieved / peak,
-                    "note": "fp32-grade GEMM = 3 bf16 tcgen05 MMAs per algorithmic MAC (hi*hi + hi*lo + lo*hi)",
-                    "avg_launch_us": avg_ms * 1e3, "traffic": None}
+        w = dict(w, name=args.workload)
+        roofline = roofline_gcn(model, w, dev) if w["model"] == "GNN" else roofline_gemm(model, w, dev)
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            n_cpu = 20 if args.workload != "cfg5" else 3
-            sps, per = cpu_reference_steps(w, n_cpu, 2, threads)
-            cpu_base = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                        "sample": f"{n_cpu} full-batch steps (B={B}) after 2 warm-up, pre-collated batch, "
-                                  f"{per * 1e3:.1f} ms/step"}
-    if rank == 0:
+            sps, per, done = cpu_reference_steps(w, 20, 2, threads, budget_s=25.0)
+            cpu_base = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "cpu": cpu_model_name(),
+                        "sample": f"{done} full-batch steps (B={B}) after 2 warm-up, pre-collated batch, "
+                                  f"{per * 1e3:.1f} ms/step, torch threads = {threads}"}
         fl = train_flops_per_sample(w)
         line = {
             "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split tcgen05, fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": DESCRIBE[args.workload], "name": args.workload, "batch_per_gpu": B,
+            "config": {"workload": w["describe"], "name": args.workload, "batch_per_gpu": B,
                        "global_batch": B * world, "params": nparams, "parallelism": f"dp{world}",
-                       "l2_policy": "operand planes of one step (131 MB for cfg2) exceed the 126 MB L2; no explicit flush",
+                       "l2_policy": "inputs larger than L2: the operand planes one step streams (131 MB for cfg2) exceed "
+                                    "the 126 MB L2; the roofline kernel is timed with an explicit 256 MB L2 flush",
                        "input_prep": "value: planes of the resident full batch are split once and reused; e2e: re-split "
                                      "every step inside the captured graph",
-                       "step": "CUDA-graph replay of fwd+bwd+clip+Adam+plane refresh"},
+                       "step": "CUDA-graph replay of fwd+bwd+clip+Adam+plane refresh"
+                               + ("; NCCL all-reduce of the flat gradient arena between the two graphs" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
             "gpu_launches": launches, "launches_per_step": step.launches_per_step,

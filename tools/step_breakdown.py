@@ -1,22 +1,19 @@
-"""Per-call device time of one eager training step (CUDA events around every C-ABI call), cfg2 by default."""
-import os, sys, json, collections
+"""Per-call device time of one eager training step (CUDA events around every C-ABI call). Usage:
+    python tools/step_breakdown.py [cfg2|cfg1|cfg3|cfg4|cfg5]"""
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import bench
-import flexynesis_b200 as fx
 from flexynesis_b200 import _lib as L
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 w = bench.WORKLOADS[name]
 dev = torch.device("cuda", 0)
-ds = fx.SyntheticMultiOmicDataset(w["dims"], w["B"], dict(w["vars"]), w["classes"], seed=0)
-class CV: pass
-cv = CV(); cv.dat, cv.features, cv.variable_types, cv.ann = ds.dat, ds.features, ds.variable_types, ds.clean_ann()
-cfg = {"latent_dim": w["latent"], "hidden_dim_factor": w["hdf"], "supervisor_hidden_dim": w["sh"], "lr": 1e-3}
-torch.manual_seed(0)
-model = fx.DirectPred(cfg, cv, list(w["vars"]), device_type="gpu").to(dev).train()
-batch = ({k: v.to(dev) for k, v in ds.dat.items()}, {k: v.to(dev) for k, v in ds.ann.items()}, None)
+prob = bench.build_problem(w, 0)
+model = bench.build_model(w, prob, dev)
+batch = bench.device_batch(prob, dev)
+model.engine().parallel_encoders = False          # serialise the modality chains so per-call times are meaningful
 for _ in range(3):
     model.fit_step(batch)
 torch.cuda.synchronize()
@@ -29,12 +26,17 @@ def wrap(fname):
         e0.record(); r = orig(*a, **k); e1.record()
         desc = fname
         if fname == "gemm":
-            desc = f"gemm M={a[0]} N={a[1]} K={a[2]} a_mn={a[4]} b_mn={a[6]} splitk={k.get('splitk',0)}"
+            desc = f"gemm M={a[0]} N={a[1]} K={a[2]} a_mn={a[4]} b_mn={a[6]} splitk={k.get('splitk',0)} epi={k.get('epi_act',0)}"
+        elif fname in ("bn_fwd", "bn_bwd"):
+            desc = f"{fname} rows={k.get('rows')} cols={k.get('cols')}"
+        elif fname in ("gcn_fwd", "gcn_bwd"):
+            desc = f"{fname} Fin={a[3] if fname == 'gcn_fwd' else a[4]}"
         records.append((desc, e0, e1))
         return r
     setattr(L, fname, f)
 for fn in ["gemm", "bn_fwd", "bn_bwd", "head_out_fwd", "head_out_bwd", "cox_fwd", "total_loss", "clip_adam",
-           "split_planes_multi", "split_planes", "col_stats"]:
+           "split_planes_multi", "split_planes", "col_stats", "gcn_fwd", "gcn_bwd", "merge_col_stats", "reparam_fwd",
+           "reparam_bwd", "row_sqnorm", "mmd_finish", "mmd_grad", "loss_weights", "randn", "triplet_fwd", "triplet_bwd"]:
     wrap(fn)
 N = 5
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -46,7 +48,7 @@ for it in range(N):
     per_iter.append([(d, a.elapsed_time(b) * 1e3) for d, a, b in records])
     tot = t0.elapsed_time(t1) * 1e3
 last = per_iter[-1]
-print(f"eager step wall (device) {tot:.1f} us; sum of calls {sum(t for _, t in last):.1f} us; {len(last)} calls")
+print(f"{name}: eager step wall (device) {tot:.1f} us; sum of calls {sum(t for _, t in last):.1f} us; {len(last)} calls")
 for i, (d, t) in enumerate(last):
     best = min(p[i][1] for p in per_iter[1:])
     fl = ""
