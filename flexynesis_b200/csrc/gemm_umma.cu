@@ -15,6 +15,8 @@
 // bf16 hi/lo planes of the result and per-tile column statistics for the BatchNorm that follows).
 #include "fxn_internal.h"
 #include "ptx.cuh"
+#include "gemm_common.cuh"
+#include <cstdlib>
 
 namespace fxn {
 
@@ -47,15 +49,6 @@ struct GemmKernelArgs {
   const float* gauss_ra; const float* gauss_rb; float gauss_inv;   // epi_act 7: exp(-max(ra[m]+rb[n]-2acc,0)*inv)
   float stats_alpha; const float* stats_alpha_dev;     // scale of the stats_mode 3 column sums
 };
-
-__device__ __forceinline__ float epi_activation(float x, int act) {
-  switch (act) {
-    case 1: return fmaxf(x, 0.f);
-    case 3: return 1.f / (1.f + __expf(-x));
-    case 6: return x > 0.f ? x : 0.2f * x;
-    default: return x;
-  }
-}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -340,38 +333,6 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 // -------------------------------------------------------------------------------------------------
 // Host side
 // -------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
-  fn = reinterpret_cast<PFN_encodeTiled>(p);
-  return fn;
-}
-
-// 2D bf16 row-major array [rows x cols], leading dimension ld (elements). Box = {64 cols, box_rows}.
-static int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) return set_error(FXN_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
-    return set_error(FXN_ERR_ARG, "bf16 plane must be 16B aligned with ld %% 8 == 0");
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error(FXN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
-  return 0;
-}
-
 // Tile width / split-K selection by a small analytic cost model (times in microseconds, B200 constants).
 // A CTA's k-block costs max(MMA issue time, operand load time); the chip moves at most ~L2_BW bytes/us from L2 to
 // the SMs, a single SM at most SM_BW; a launch costs its waves times the CTA time.
@@ -430,6 +391,12 @@ extern "C" int fxn_gemm(const fxn_gemm_desc* d, void* stream_) {
   if (!d->a_hi || !d->b_hi || (d->nterms == 3 && (!d->a_lo || !d->b_lo)))
     return set_error(FXN_ERR_ARG, "fxn_gemm: missing operand plane");
   if (!d->C && !d->c_hi) return set_error(FXN_ERR_ARG, "fxn_gemm: no output");
+  {
+    // FXN_GEMM_KERNEL=1 selects the one-tile-per-CTA kernel below (kept as the A/B reference); default is the
+    // persistent CTA-pair kernel of gemm_umma2.cu
+    static const int which = [] { const char* e = getenv("FXN_GEMM_KERNEL"); return e ? atoi(e) : 2; }();
+    if (which != 1) return gemm2_dispatch(d, stream);
+  }
 
   GemmKernelArgs p;
   p.M = d->M; p.N = d->N; p.K = d->K;
@@ -497,11 +464,11 @@ extern "C" int fxn_gemm(const fxn_gemm_desc* d, void* stream_) {
   const long long a_rows = p.a_mn ? d->K : d->M, a_cols = p.a_mn ? d->M : d->K;
   const long long b_rows = p.b_mn ? d->K : d->N, b_cols = p.b_mn ? d->N : d->K;
   const int a_box = p.a_mn ? BK : BM, b_box = p.b_mn ? BK : p.bn;
-  if ((rc = make_map(&ta_hi, d->a_hi, a_rows, a_cols, d->lda, a_box))) return rc;
-  if ((rc = make_map(&tb_hi, d->b_hi, b_rows, b_cols, d->ldb, b_box))) return rc;
+  if ((rc = make_tensor_map(&ta_hi, d->a_hi, a_rows, a_cols, d->lda, a_box))) return rc;
+  if ((rc = make_tensor_map(&tb_hi, d->b_hi, b_rows, b_cols, d->ldb, b_box))) return rc;
   if (nplanes == 2) {
-    if ((rc = make_map(&ta_lo, d->a_lo, a_rows, a_cols, d->lda, a_box))) return rc;
-    if ((rc = make_map(&tb_lo, d->b_lo, b_rows, b_cols, d->ldb, b_box))) return rc;
+    if ((rc = make_tensor_map(&ta_lo, d->a_lo, a_rows, a_cols, d->lda, a_box))) return rc;
+    if ((rc = make_tensor_map(&tb_lo, d->b_lo, b_rows, b_cols, d->ldb, b_box))) return rc;
   } else {
     ta_lo = ta_hi;
     tb_lo = tb_hi;

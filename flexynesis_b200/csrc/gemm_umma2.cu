@@ -1,0 +1,756 @@
+// gemm2: persistent tcgen05 GEMM, C[M,N] = sum over bf16 split terms of A[M,K] * B[N,K]^T, one kernel for every dense
+// contraction of the training step (same operand conventions as gemm_umma.cu, which stays as the reference path).
+//
+// What changed against gemm_umma.cu and why (profiles/r01_*):
+//  * CTA PAIRS (tcgen05 cta_group::2, cluster 2x1x1): a pair computes a 256 x bn tile; each CTA stages its own 128 rows
+//    of A and only HALF of the B tile, the MMA reads both halves through the pair's shared-memory window. The mid-size
+//    GEMMs of the step (M = 4096, K = 5000, N = 512) are bound by L2 -> SM operand traffic, not by the tensor pipe:
+//    128x128 tiles move 650 MB per launch, pair tiles of 256x256 move 324 MB.
+//  * PERSISTENT CTAs with a DOUBLE-BUFFERED TMEM accumulator (2 x bn columns): the epilogue of tile i (TMEM -> registers
+//    -> global) overlaps the TMA/MMA main loop of tile i+1; the small-K GEMMs (dgrad K = 128..512, decoder, Gram) were
+//    epilogue-serialised at one tile per CTA launch.
+//  * CHUNKED EPILOGUE: 32-column chunks are transposed through a 4.5 KB per-warp staging buffer instead of a full
+//    128 x bn fp32 tile, which frees the shared memory for pipeline stages.
+//  * STREAM-K for plain fp32 outputs (the wgrads, K = batch): the (tile, k-block) space is cut into equal contiguous
+//    ranges, one per CTA pair, partial tiles are combined with fp32 reductions into the zeroed C.
+//
+// Roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA of the pair only) + TMEM
+// allocation, warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+#include "fxn_internal.h"
+#include "ptx.cuh"
+#include "gemm_common.cuh"
+#include <cstdlib>
+#include <cstdio>
+#include <cmath>
+
+namespace fxn {
+
+constexpr int G2_THREADS = 192;
+constexpr int G2_BM = 128;          // rows of A per CTA
+constexpr int G2_BK = 64;           // one 128-byte swizzle atom of bf16 along K
+constexpr int G2_UK = 16;
+constexpr int G2_MAX_STAGES = 8;
+constexpr int G2_CHUNK = 32;        // epilogue column chunk
+constexpr int G2_STG_LD = 36;       // staging row stride in floats (16-byte aligned rows, spreads banks)
+constexpr int G2_STG_BYTES = 4 * 32 * G2_STG_LD * 4;
+constexpr int G2_MAX_DYN_SMEM = 229376;   // 227 KB per CTA minus the static shared memory (barriers, statistics exchange)
+
+struct Gemm2Args {
+  int M, N, K;
+  int bn;                 // tile width of the CTA group (columns of C)
+  int a_mn, b_mn;
+  int nterms;
+  int stages;
+  int streamk;            // 1: equal (tile, k-block) ranges per group, reductions into zeroed C
+  int tiles_m, tiles_n, kb_total;
+  uint32_t tmem_cols;
+  float* C; long long ldc;
+  const float* bias;
+  __nv_bfloat16* c_hi; __nv_bfloat16* c_lo; long long ldp;
+  float* colstats; int stats_mode;
+  int epi_act; int accumulate;
+  float alpha; const float* alpha_dev;
+  const float* mse_x; long long ldx; float* mse_acc;
+  const float* gauss_ra; const float* gauss_rb; float gauss_inv;
+  float stats_alpha; const float* stats_alpha_dev;
+  int trace;
+  int epi_variant;        // index of the specialised epilogue loop for interior chunks, -1 = generic only
+};
+
+// ---- PTX pieces that differ between cta_group::1 and ::2 ----
+template <int CG> __device__ __forceinline__ void g2_tmem_alloc(uint32_t* dst, uint32_t ncols) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG> __device__ __forceinline__ void g2_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void g2_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if constexpr (CG == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+                 "r"(idesc), "r"(acc) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+                 "r"(idesc), "r"(acc) : "memory");
+  }
+}
+// arrive on the barrier at this shared-memory offset in every CTA of the group once the issued MMAs have retired
+template <int CG> __device__ __forceinline__ void g2_commit(uint64_t* bar) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)), "h"(mask) : "memory");
+  }
+}
+// TMA tile load whose byte count is credited to the LEADER CTA's barrier (peer bit of the address cleared)
+template <int CG>
+__device__ __forceinline__ void g2_tma_load(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if constexpr (CG == 1) {
+    tma_load_2d(smem_dst, m, bar, c0, c1);
+  } else {
+    const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1) : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier with this local offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+// ---- optional timeline of CTA 0 / CTA 1 (clock64 stamps), enabled with FXN_GEMM_TRACE=1; read by fxn_debug_gemm_trace ----
+__device__ long long g2_trace[2][16];
+#define G2_STAMP(slot)                                                        \
+  do {                                                                        \
+    if (p.trace && blockIdx.x < 2) g2_trace[blockIdx.x][slot] = clock64();    \
+  } while (0)
+
+// ---- work decomposition shared by the three roles ----
+struct Segment { int mt, nt, kb0, kb1; };
+struct WorkIter {
+  long long u, end;     // stream-K: position / end in the (tile, k-block) space; tile mode: tile index / tile count
+  int step;             // tile mode: stride
+  int kb_total, tiles_n, streamk;
+  __device__ __forceinline__ WorkIter(const Gemm2Args& p, int group, int ngroups) {
+    kb_total = p.kb_total; tiles_n = p.tiles_n; streamk = p.streamk;
+    const long long tiles = static_cast<long long>(p.tiles_m) * p.tiles_n;
+    if (streamk) {
+      const long long units = tiles * kb_total;
+      u = units * group / ngroups;
+      end = units * (group + 1) / ngroups;
+      step = 0;
+    } else {
+      u = group; end = tiles; step = ngroups;
+    }
+  }
+  __device__ __forceinline__ bool next(Segment& s) {
+    if (u >= end) return false;
+    if (streamk) {
+      const long long tile = u / kb_total;
+      s.kb0 = static_cast<int>(u - tile * kb_total);
+      const long long room = end - u;
+      s.kb1 = static_cast<int>(room < kb_total - s.kb0 ? s.kb0 + room : kb_total);
+      s.mt = static_cast<int>(tile / tiles_n); s.nt = static_cast<int>(tile - static_cast<long long>(s.mt) * tiles_n);
+      u += s.kb1 - s.kb0;
+    } else {
+      s.mt = static_cast<int>(u / tiles_n); s.nt = static_cast<int>(u - static_cast<long long>(s.mt) * tiles_n);
+      s.kb0 = 0; s.kb1 = kb_total;
+      u += step;
+    }
+    return true;
+  }
+};
+
+
+// explicit shared-window accesses: a staging pointer that travels through a struct loses its address space and the
+// compiler falls back to generic LD/ST (measured: 4x slower epilogue)
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+// ---- epilogue inner loop: 16 passes over a staged 32 x 32 chunk, lane = (row parity, column pair) ----
+struct EpiRowCtx {
+  uint32_t stg;           // shared-window address of this lane's first staged element (row rr, columns 2cp, 2cp + 1)
+  int mbase, rr, col, rows_valid, padN;
+  bool ok0, ok1, c_vec2, x_vec2, atomic_out;
+  float alpha, b0, b1, rb0, rb1;
+};
+
+// RT = true: every mode is read from the descriptor at run time and every access is bounds-checked (edge chunks and
+// rare mode combinations). RT = false: modes are template constants and the chunk is known to be interior (32 valid
+// rows, 32 valid columns, vector-aligned), so the loop body is a handful of instructions.
+// CMODE: 0 no fp32 output, 1 store, 2 accumulate, 3 reduction (stream-K). STATS: 0 none, 1 sums, 2 sums + M2, 3 column sums.
+template <bool RT, int ACT, int CMODE, bool PLANES, int STATS, bool MSE>
+__device__ __forceinline__ void epi_rows(const Gemm2Args& p, const EpiRowCtx& cx, float& s0, float& s1, float& sq_acc) {
+  const int act = RT ? p.epi_act : ACT;
+  const int cmode = RT ? (p.C == nullptr ? 0 : (cx.atomic_out ? 3 : (p.accumulate ? 2 : 1))) : CMODE;
+  const bool planes = RT ? (p.c_hi != nullptr) : PLANES;
+  const int stats = RT ? p.stats_mode : STATS;
+  const bool mse = RT ? (p.mse_x != nullptr) : MSE;
+  const long long row0 = cx.mbase + cx.rr;
+  float* cptr = cmode ? p.C + row0 * p.ldc + cx.col : nullptr;
+  const float* xptr = mse ? p.mse_x + row0 * p.ldx + cx.col : nullptr;
+  __nv_bfloat16* hptr = planes ? p.c_hi + row0 * p.ldp + cx.col : nullptr;
+  __nv_bfloat16* lptr = planes ? p.c_lo + row0 * p.ldp + cx.col : nullptr;
+  const float* gra = (act == 7) ? p.gauss_ra : nullptr;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int r = 2 * i + cx.rr;
+    const bool rok = RT ? (r < cx.rows_valid) : true;
+    const bool ok0 = RT ? cx.ok0 : true, ok1 = RT ? cx.ok1 : true;
+    float2 x = lds_f2(cx.stg + 2 * i * G2_STG_LD * 4);
+    x.x = fmaf(x.x, cx.alpha, cx.b0);
+    x.y = fmaf(x.y, cx.alpha, cx.b1);
+    if (act == 7) {
+      const float ra = __ldg(gra + (RT ? min(cx.mbase + r, p.M - 1) : cx.mbase + r));
+      x.x = __expf(-fmaxf(ra + cx.rb0 - 2.f * x.x, 0.f) * p.gauss_inv);
+      x.y = __expf(-fmaxf(ra + cx.rb1 - 2.f * x.y, 0.f) * p.gauss_inv);
+    } else if (act == 1) {
+      x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f);
+    } else if (act == 6) {
+      x.x = x.x > 0.f ? x.x : 0.2f * x.x; x.y = x.y > 0.f ? x.y : 0.2f * x.y;
+    } else if (act == 3) {
+      x.x = 1.f / (1.f + __expf(-x.x)); x.y = 1.f / (1.f + __expf(-x.y));
+    }
+    if (RT) { if (!ok0) x.x = 0.f; if (!ok1) x.y = 0.f; }
+    if (cmode != 0 && rok) {
+      float* cp_ = cptr + static_cast<long long>(2 * i) * p.ldc;
+      if (cmode == 3) {
+        if (ok0) atomicAdd(cp_, x.x);
+        if (ok1) atomicAdd(cp_ + 1, x.y);
+      } else if (!RT || (ok1 && cx.c_vec2)) {
+        float2 o = x;
+        if (cmode == 2) { const float2 old = *reinterpret_cast<const float2*>(cp_); o.x += old.x; o.y += old.y; }
+        *reinterpret_cast<float2*>(cp_) = o;
+      } else {
+        if (ok0) cp_[0] = cmode == 2 ? cp_[0] + x.x : x.x;
+        if (ok1) cp_[1] = cmode == 2 ? cp_[1] + x.y : x.y;
+      }
+    }
+    if (mse) {
+      // fused Decoder output: x = x_hat; accumulate (x_hat - x)^2, continue with G = (x_hat - x) x_hat (1 - x_hat)
+      float t0 = 0.f, t1 = 0.f;
+      if (rok) {
+        const float* xp = xptr + static_cast<long long>(2 * i) * p.ldx;
+        if (!RT || (ok1 && cx.x_vec2)) { const float2 t = __ldg(reinterpret_cast<const float2*>(xp)); t0 = t.x; t1 = t.y; }
+        else { if (ok0) t0 = __ldg(xp); if (ok1) t1 = __ldg(xp + 1); }
+      }
+      const float d0 = (rok && ok0) ? x.x - t0 : 0.f, d1 = (rok && ok1) ? x.y - t1 : 0.f;
+      sq_acc = fmaf(d0, d0, sq_acc);
+      sq_acc = fmaf(d1, d1, sq_acc);
+      x.x = d0 * x.x * (1.f - x.x);
+      x.y = d1 * x.y * (1.f - x.y);
+    }
+    if (planes && rok && (!RT || cx.col < cx.padN)) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(x.x, h0, l0);
+      split_bf16(x.y, h1, l1);
+      const long long off = static_cast<long long>(2 * i) * p.ldp;
+      *reinterpret_cast<__nv_bfloat162*>(hptr + off) = __halves2bfloat162(h0, h1);
+      *reinterpret_cast<__nv_bfloat162*>(lptr + off) = __halves2bfloat162(l0, l1);
+    }
+    if (stats != 0) {
+      if (rok) { s0 += x.x; s1 += x.y; }
+      if (stats == 2) sts_f2(cx.stg + 2 * i * G2_STG_LD * 4, x);   // the M2 pass reads it back
+    }
+  }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const Gemm2Args p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[G2_MAX_STAGES];
+  __shared__ uint64_t empty_bar[G2_MAX_STAGES];
+  __shared__ uint64_t tfull_bar[2];
+  __shared__ uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_stat[4][2][G2_CHUNK];     // cross-warp merge of column statistics
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int group = blockIdx.x / CG, ngroups = gridDim.x / CG;
+  const int nplanes = (p.nterms == 3) ? 2 : 1;
+  const int bnl = p.bn / CG;                                   // rows of the B tile staged by this CTA
+  const uint32_t a_bytes = G2_BM * G2_BK * 2;
+  const uint32_t b_bytes = static_cast<uint32_t>(bnl) * G2_BK * 2;
+  const uint32_t stage_bytes = nplanes * (a_bytes + b_bytes);
+  float* stg_all = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
+
+  if (threadIdx.x == 0) G2_STAMP(0);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (nplanes == 2) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * CG); }
+    fence_mbar_init();
+  }
+  if (warp == 1) g2_tmem_alloc<CG>(&tmem_base_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // peer barriers are initialised before anyone signals them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0) G2_STAMP(1);
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane, every CTA of the group) =====================
+    if (lane == 0) {
+      WorkIter it(p, group, ngroups);
+      Segment sg;
+      int stage = 0;
+      uint32_t phase = 0;
+      while (it.next(sg)) {
+        const int m0 = (sg.mt * CG + static_cast<int>(rank)) * G2_BM;
+        const int n0 = sg.nt * p.bn + static_cast<int>(rank) * bnl;
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes * CG);
+          const int k0 = kb * G2_BK;
+          for (int pl = 0; pl < nplanes; ++pl) {
+            uint8_t* sa = st + pl * a_bytes;
+            uint8_t* sb = st + nplanes * a_bytes + pl * b_bytes;
+            const CUtensorMap* ta = pl ? &tmA_lo : &tmA_hi;
+            const CUtensorMap* tb = pl ? &tmB_lo : &tmB_hi;
+            if (p.a_mn == 0) {
+              g2_tma_load<CG>(sa, ta, &full_bar[stage], k0, m0);                       // box {64 k, 128 rows}
+            } else {
+              for (int a = 0; a < G2_BM / 64; ++a)                                     // box {64 m, 64 k rows}
+                g2_tma_load<CG>(sa + a * (G2_BK * 128), ta, &full_bar[stage], m0 + a * 64, k0);
+            }
+            if (p.b_mn == 0) {
+              g2_tma_load<CG>(sb, tb, &full_bar[stage], k0, n0);                       // box {64 k, bnl rows}
+            } else {
+              for (int a = 0; a < bnl / 64; ++a)
+                g2_tma_load<CG>(sb + a * (G2_BK * 128), tb, &full_bar[stage], n0 + a * 64, k0);
+            }
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (kb == sg.kb0) G2_STAMP(2);        // first load of the (last) segment issued
+        }
+      }
+      G2_STAMP(3);                              // all loads issued
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one thread of the leader CTA =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(G2_BM * CG, p.bn, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? G2_BK * 128 : 16, b_lbo = p.b_mn ? G2_BK * 128 : 16;
+      const uint32_t a_kstep = p.a_mn ? G2_UK * 128 : G2_UK * 2, b_kstep = p.b_mn ? G2_UK * 128 : G2_UK * 2;
+      WorkIter it(p, group, ngroups);
+      Segment sg;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_iter = 0;
+      while (it.next(sg)) {
+        const uint32_t as = tile_iter & 1, aphase = (tile_iter >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);              // epilogues of both CTAs have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * static_cast<uint32_t>(p.bn);
+        uint32_t acc = 0;
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          if (kb == sg.kb0 && tile_iter == 0) G2_STAMP(4);   // first stage landed
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sa_hi = st, sa_lo = st + a_bytes;
+          const uint32_t sb_hi = st + nplanes * a_bytes, sb_lo = sb_hi + b_bytes;
+#pragma unroll
+          for (int kk = 0; kk < G2_BK / G2_UK; ++kk) {
+            const uint64_t da_hi = umma_smem_desc_sw128(sa_hi + kk * a_kstep, a_lbo, 1024);
+            const uint64_t db_hi = umma_smem_desc_sw128(sb_hi + kk * b_kstep, b_lbo, 1024);
+            if (nplanes == 2) {
+              const uint64_t da_lo = umma_smem_desc_sw128(sa_lo + kk * a_kstep, a_lbo, 1024);
+              const uint64_t db_lo = umma_smem_desc_sw128(sb_lo + kk * b_kstep, b_lbo, 1024);
+              g2_mma<CG>(tmem_acc, da_lo, db_hi, idesc, acc);   // small terms first
+              acc = 1;
+              g2_mma<CG>(tmem_acc, da_hi, db_lo, idesc, acc);
+            }
+            g2_mma<CG>(tmem_acc, da_hi, db_hi, idesc, acc);
+            acc = 1;
+          }
+          g2_commit<CG>(&empty_bar[stage]);                    // frees this stage in every CTA of the group
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        g2_commit<CG>(&tfull_bar[as]);                         // accumulator complete -> both epilogues
+        if (tile_iter == 0) G2_STAMP(5);                     // first tile fully issued
+        ++tile_iter;
+      }
+      G2_STAMP(6);                                           // all MMAs issued
+    }
+  } else {
+    // ===================== Epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
+    const int q = warp & 3;
+    const uint32_t stg_s = smem_u32(stg_all + (warp - 2) * (32 * G2_STG_LD));
+    const int rr = lane >> 4, cp = lane & 15;                 // transposed layout: 2 rows x 16 column pairs per pass
+    const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
+    const float sscale = p.stats_alpha * (p.stats_alpha_dev ? __ldg(p.stats_alpha_dev) : 1.f);
+    const int padN = (p.N + 7) & ~7;
+    const bool c_vec2 = p.C && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0) && (p.ldc % 2 == 0);
+    const bool x_vec2 = p.mse_x && ((reinterpret_cast<uintptr_t>(p.mse_x) & 7) == 0) && (p.ldx % 2 == 0);
+    WorkIter it(p, group, ngroups);
+    Segment sg;
+    uint32_t tile_iter = 0;
+    while (it.next(sg)) {
+      const uint32_t as = tile_iter & 1, aphase = (tile_iter >> 1) & 1;
+      const int mbase = (sg.mt * CG + static_cast<int>(rank)) * G2_BM + q * 32;   // first row of this warp's quarter
+      const int n0 = sg.nt * p.bn;
+      const int rows_valid = max(0, min(32, p.M - mbase));
+      const bool add_bias = p.bias != nullptr && sg.kb0 == 0;
+      const bool atomic_out = p.streamk != 0;
+      mbar_wait(&tfull_bar[as], aphase);
+      if (warp == 2 && lane == 0 && tile_iter == 0) G2_STAMP(7);   // first accumulator ready
+      tc_fence_after();
+      float sq_acc = 0.f;
+      const int ncols_tile = min(p.bn, p.N - n0);                        // valid columns of this tile (may be <= 0 never)
+      const int nchunks = (min(p.bn, padN - n0) + G2_CHUNK - 1) / G2_CHUNK;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = ch * G2_CHUNK;
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + as * static_cast<uint32_t>(p.bn) + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(c0);
+        if (p.bn - c0 >= 32) {
+          tmem_ld_32x32(taddr, v);
+        } else {
+          tmem_ld_32x16(taddr, v);
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0;
+        }
+        tmem_ld_wait();
+        if (ch == nchunks - 1) {
+          // every accumulator value of this tile is in registers: hand the TMEM stage back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+        }
+        __syncwarp();
+        // lane = row: 32 consecutive columns -> staging (row stride 36 floats)
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          sts_f4(stg_s + (lane * G2_STG_LD + j) * 4, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                 __uint_as_float(v[j + 3]));
+        __syncwarp();
+        // transposed passes: lane handles columns (col, col + 1) of rows 2i + rr
+        const int col = n0 + c0 + 2 * cp;
+        const bool ok0 = col < p.N, ok1 = col + 1 < p.N;
+        float b0 = 0.f, b1 = 0.f, rb0 = 0.f, rb1 = 0.f;
+        if (add_bias) { if (ok0) b0 = __ldg(p.bias + col); if (ok1) b1 = __ldg(p.bias + col + 1); }
+        if (p.epi_act == 7) { rb0 = __ldg(p.gauss_rb + min(col, p.N - 1)); rb1 = __ldg(p.gauss_rb + min(col + 1, p.N - 1)); }
+        float s0 = 0.f, s1 = 0.f;
+        EpiRowCtx cx;
+        cx.stg = stg_s + (rr * G2_STG_LD + 2 * cp) * 4;
+        cx.mbase = mbase; cx.rr = rr; cx.col = col; cx.rows_valid = rows_valid; cx.ok0 = ok0; cx.ok1 = ok1;
+        cx.alpha = alpha; cx.b0 = b0; cx.b1 = b1; cx.rb0 = rb0; cx.rb1 = rb1; cx.padN = padN;
+        cx.c_vec2 = c_vec2; cx.x_vec2 = x_vec2; cx.atomic_out = atomic_out;
+        const bool interior = rows_valid == 32 && n0 + c0 + G2_CHUNK <= p.N && (c_vec2 || p.C == nullptr) &&
+                              (x_vec2 || p.mse_x == nullptr);
+        switch (interior ? p.epi_variant : -1) {
+          //                         ACT CMODE PLANES STATS MSE
+          case 0:  epi_rows<false, 0, 1, false, 0, false>(p, cx, s0, s1, sq_acc); break;   // plain fp32 output
+          case 1:  epi_rows<false, 0, 1, false, 2, false>(p, cx, s0, s1, sq_acc); break;   // MLP layer_1 forward (+ BN partials)
+          case 2:  epi_rows<false, 6, 1, false, 2, false>(p, cx, s0, s1, sq_acc); break;   // Encoder/Decoder hidden forward
+          case 3:  epi_rows<false, 0, 1, true, 0, false>(p, cx, s0, s1, sq_acc); break;    // fp32 + planes
+          case 4:  epi_rows<false, 0, 0, true, 0, false>(p, cx, s0, s1, sq_acc); break;    // planes only
+          case 5:  epi_rows<false, 0, 0, true, 3, false>(p, cx, s0, s1, sq_acc); break;    // planes + column sums
+          case 6:  epi_rows<false, 0, 3, false, 0, false>(p, cx, s0, s1, sq_acc); break;   // stream-K reductions
+          case 7:  epi_rows<false, 0, 2, false, 0, false>(p, cx, s0, s1, sq_acc); break;   // C +=
+          case 8:  epi_rows<false, 3, 0, true, 3, true>(p, cx, s0, s1, sq_acc); break;     // Decoder output + MSE
+          case 9:  epi_rows<false, 7, 0, true, 3, false>(p, cx, s0, s1, sq_acc); break;    // Gaussian-kernel Gram
+          case 10: epi_rows<false, 0, 1, true, 3, false>(p, cx, s0, s1, sq_acc); break;    // fp32 + planes + column sums
+          case 11: epi_rows<false, 6, 1, false, 0, false>(p, cx, s0, s1, sq_acc); break;   // hidden forward, eval mode
+          default: epi_rows<true, 0, 0, false, 0, false>(p, cx, s0, s1, sq_acc); break;    // edges / anything else
+        }
+        if (p.stats_mode != 0) {
+          // column sums over this warp's 32 rows (combine the two row-parity halves)
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          if (p.stats_mode == 3) {
+            if (rr == 0) {
+              if (ok0) atomicAdd(p.colstats + col, s0 * sscale);
+              if (ok1) atomicAdd(p.colstats + col + 1, s1 * sscale);
+            }
+          } else {
+            float m20 = 0.f, m21 = 0.f;
+            if (p.stats_mode == 2 && rows_valid > 0) {
+              const float mu0 = s0 / static_cast<float>(rows_valid), mu1 = s1 / static_cast<float>(rows_valid);
+              __syncwarp();
+              for (int i = 0; i < 16; ++i) {
+                const int r = 2 * i + rr;
+                if (r < rows_valid) {
+                  const float2 x = lds_f2(stg_s + (r * G2_STG_LD + 2 * cp) * 4);
+                  m20 = fmaf(x.x - mu0, x.x - mu0, m20);
+                  m21 = fmaf(x.y - mu1, x.y - mu1, m21);
+                }
+              }
+              m20 += __shfl_xor_sync(0xffffffffu, m20, 16);
+              m21 += __shfl_xor_sync(0xffffffffu, m21, 16);
+            }
+            // merge the four 32-row quarters of this CTA's 128 rows (Chan) -> one partial per 128-row tile
+            if (rr == 0) {
+              s_stat[q][0][2 * cp] = s0; s_stat[q][0][2 * cp + 1] = s1;
+              s_stat[q][1][2 * cp] = m20; s_stat[q][1][2 * cp + 1] = m21;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (q == 0 && lane < 32) {
+              const int c = n0 + c0 + lane;
+              const int tile_row0 = (sg.mt * CG + static_cast<int>(rank)) * G2_BM;
+              if (c < p.N && tile_row0 < p.M) {        // the second CTA of the last pair may own no valid row at all
+                float tn = 0.f, tm = 0.f, tm2 = 0.f, tsum = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float nk = static_cast<float>(max(0, min(32, p.M - (tile_row0 + k * 32))));
+                  if (nk > 0.f) {
+                    const float sk = s_stat[k][0][lane];
+                    const float delta = sk / nk - tm;
+                    const float nn = tn + nk;
+                    tm += delta * nk / nn;
+                    tm2 += s_stat[k][1][lane] + delta * delta * tn * nk / nn;
+                    tn = nn;
+                    tsum += sk;
+                  }
+                }
+                const long long t128 = tile_row0 / G2_BM;
+                float* dst = p.colstats + (t128 * 2) * p.N + c;
+                dst[0] = tsum;
+                dst[p.N] = tm2;
+              }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+        }
+        __syncwarp();
+      }
+      if (p.mse_x != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq_acc += __shfl_xor_sync(0xffffffffu, sq_acc, o);
+        if (lane == 0) atomicAdd(p.mse_acc, sq_acc);
+      }
+      (void)ncols_tile;
+      if (warp == 2 && lane == 0 && tile_iter == 0) G2_STAMP(8);   // first tile stored
+      ++tile_iter;
+    }
+    if (warp == 2 && lane == 0) G2_STAMP(9);                       // all tiles stored
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();      // no CTA leaves (or frees TMEM) while its peer may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    g2_tmem_dealloc<CG>(tmem_base, p.tmem_cols);
+  }
+  if (threadIdx.x == 0) G2_STAMP(10);
+}
+
+}  // namespace fxn
+
+using namespace fxn;
+
+namespace {
+
+struct Plan { int cg, bn, stages, streamk, groups, tiles_m, tiles_n; };
+
+// Pick CTA-group size, tile width and scheduling mode with a small analytic cost model (SM cycles; constants from the
+// pipeline traces in profiles/r01_gemm2_trace.log). Tile mode keeps the whole K per tile (needed by every fused
+// epilogue); stream-K needs a plain fp32 C.
+Plan make_plan(int M, int N, int K, int nterms, int b_mn, bool plain_c, int force_bn) {
+  const int nplanes = nterms == 3 ? 2 : 1;
+  const int kb_total = (K + G2_BK - 1) / G2_BK;
+  const int cg = M > G2_BM ? 2 : 1;
+  const int unit = b_mn ? 64 * cg : 16 * cg;                   // per-CTA B rows: multiple of 64 (MN-major) or 16
+  const int max_groups = 148 / cg;
+  const int tiles_m = (M + G2_BM * cg - 1) / (G2_BM * cg);
+  const double SETUP = 3500.0, EPI_CHUNK = 1250.0, SM_BW = 90.0, L2_BW = 6000.0, MEMSET = 4000.0;
+  Plan best{};
+  double best_t = 1e300;
+  for (int bn = unit; bn <= 256; bn += unit) {
+    if (force_bn > 0 && bn != (force_bn + unit - 1) / unit * unit && !(bn == 256 && force_bn > 256)) continue;
+    const int tiles_n = (N + bn - 1) / bn;
+    if (tiles_n > 1 && (tiles_n - 1) * bn >= N) continue;
+    if (force_bn <= 0 && tiles_n > 1 && bn < 64) continue;     // narrow tiles only when one tile covers N
+    const int stage_bytes = nplanes * (G2_BM * G2_BK * 2 + (bn / cg) * G2_BK * 2);
+    const int budget = G2_MAX_DYN_SMEM - 1024 - G2_STG_BYTES;
+    int stages = budget / stage_bytes;
+    if (stages > G2_MAX_STAGES) stages = G2_MAX_STAGES;
+    if (stages < 2) continue;
+    const long long tiles = static_cast<long long>(tiles_m) * tiles_n;
+    const double t_mma = nterms * 4.0 * (bn / 2.0);
+    const double t_epi = EPI_CHUNK * ((bn + 31) / 32);
+    for (int mode = 0; mode < 2; ++mode) {                     // 0 = whole tiles, 1 = stream-K
+      if (mode == 1 && (!plain_c || kb_total < 4)) break;
+      int groups;
+      double t;
+      if (mode == 0) {
+        groups = static_cast<int>(tiles < max_groups ? tiles : max_groups);
+        const double t_load = fmax(stage_bytes / SM_BW, static_cast<double>(stage_bytes) * groups * cg / L2_BW);
+        const double t_main = kb_total * fmax(t_mma, t_load) + (stages < 3 ? 0.25 * kb_total * t_load : 0.0);
+        const long long tpg = (tiles + groups - 1) / groups;
+        t = SETUP + t_main + (tpg - 1) * fmax(t_main, t_epi) + t_epi;
+      } else {
+        const long long units = tiles * kb_total;
+        const long long g = units / 2;
+        groups = static_cast<int>(g < max_groups ? g : max_groups);
+        if (groups < 1) break;
+        const double kb_per = static_cast<double>(units) / groups;
+        const double t_load = fmax(stage_bytes / SM_BW, static_cast<double>(stage_bytes) * groups * cg / L2_BW);
+        const double segs = 1.0 + (kb_per < kb_total ? 1.0 : kb_per / kb_total);
+        t = SETUP + MEMSET + kb_per * fmax(t_mma, t_load) + segs * 1.3 * t_epi;
+      }
+      if (t < best_t) {
+        best_t = t;
+        best.cg = cg; best.bn = bn; best.stages = stages; best.streamk = mode; best.groups = groups;
+        best.tiles_m = tiles_m; best.tiles_n = tiles_n;
+      }
+    }
+  }
+  return best;
+}
+
+template <int CG>
+cudaError_t launch_gemm2(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
+                         const CUtensorMap& tb_lo, const Gemm2Args& p, int groups, int smem_bytes, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_MAX_DYN_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(groups * CG, 1, 1);
+  cfg.blockDim = dim3(G2_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm2_kernel<CG>, ta_hi, ta_lo, tb_hi, tb_lo, p);
+}
+
+}  // namespace
+
+namespace fxn {
+
+int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
+  Gemm2Args p{};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.a_mn = d->a_mn_major ? 1 : 0;
+  p.b_mn = d->b_mn_major ? 1 : 0;
+  p.nterms = d->nterms;
+  const bool plain_c = (d->splitk < 0 || d->splitk > 1) && d->C && !d->c_hi && !d->colstats && !d->epi_act && !d->accumulate && !d->mse_x;
+  const Plan pl = make_plan(d->M, d->N, d->K, d->nterms, p.b_mn, plain_c, d->block_n);
+  if (pl.stages < 1) return set_error(FXN_ERR_ARG, "fxn_gemm: tile does not fit in shared memory");
+  p.bn = pl.bn;
+  p.stages = pl.stages;
+  p.streamk = pl.streamk;
+  p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n;
+  p.kb_total = (d->K + G2_BK - 1) / G2_BK;
+  if (p.stages > p.kb_total && !p.streamk && static_cast<long long>(pl.tiles_m) * pl.tiles_n <= pl.groups)
+    p.stages = p.kb_total < 1 ? 1 : p.kb_total;                 // one tile per group: no need for more stages than k-blocks
+  uint32_t tc = 32;
+  while (tc < static_cast<uint32_t>(2 * p.bn)) tc <<= 1;
+  p.tmem_cols = tc;
+  p.C = d->C; p.ldc = d->ldc;
+  p.bias = d->bias;
+  p.c_hi = static_cast<__nv_bfloat16*>(d->c_hi);
+  p.c_lo = static_cast<__nv_bfloat16*>(d->c_lo);
+  p.ldp = d->ldp;
+  p.colstats = d->colstats;
+  p.stats_mode = d->colstats ? (d->stats_mode ? d->stats_mode : 2) : 0;
+  if (p.c_hi && (!p.c_lo || d->ldp % 8 != 0 || (reinterpret_cast<uintptr_t>(d->c_hi) & 15) ||
+                 (reinterpret_cast<uintptr_t>(d->c_lo) & 15)))
+    return set_error(FXN_ERR_ARG, "fxn_gemm: output planes need both pointers, 16B alignment and ldp %% 8 == 0");
+  p.epi_act = d->epi_act;
+  p.accumulate = d->accumulate;
+  p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
+  p.alpha_dev = d->alpha_dev;
+  p.mse_x = d->mse_x; p.ldx = d->ldx; p.mse_acc = d->mse_acc;
+  if (p.mse_x && (!p.mse_acc || (p.stats_mode && p.stats_mode != 3)))
+    return set_error(FXN_ERR_ARG, "fxn_gemm: fused MSE needs mse_acc and excludes per-tile statistics");
+  p.gauss_ra = d->gauss_ra; p.gauss_rb = d->gauss_rb; p.gauss_inv = d->gauss_inv;
+  if (p.epi_act == 7 && (!p.gauss_ra || !p.gauss_rb)) return set_error(FXN_ERR_ARG, "fxn_gemm: epi_act 7 needs row norms");
+  p.stats_alpha = d->stats_alpha == 0.f ? 1.f : d->stats_alpha;
+  p.stats_alpha_dev = d->stats_alpha_dev;
+  {
+    const int cmode = !d->C ? 0 : (p.streamk ? 3 : (d->accumulate ? 2 : 1));
+    const int act = p.epi_act, st = p.stats_mode;
+    const bool pl_ = p.c_hi != nullptr, ms = p.mse_x != nullptr;
+    struct V { int act, cmode, planes, stats, mse; };
+    static const V table[12] = {{0, 1, 0, 0, 0}, {0, 1, 0, 2, 0}, {6, 1, 0, 2, 0}, {0, 1, 1, 0, 0}, {0, 0, 1, 0, 0}, {0, 0, 1, 3, 0},
+                                {0, 3, 0, 0, 0}, {0, 2, 0, 0, 0}, {3, 0, 1, 3, 1}, {7, 0, 1, 3, 0}, {0, 1, 1, 3, 0}, {6, 1, 0, 0, 0}};
+    p.epi_variant = -1;
+    for (int i = 0; i < 12; ++i)
+      if (table[i].act == act && table[i].cmode == cmode && table[i].planes == (pl_ ? 1 : 0) && table[i].stats == st &&
+          table[i].mse == (ms ? 1 : 0))
+        p.epi_variant = i;
+    if (const char* e = getenv("FXN_GEMM_GENERIC_EPILOGUE")) if (atoi(e)) p.epi_variant = -1;
+  }
+  static const int trace = [] { const char* e = getenv("FXN_GEMM_TRACE"); return e ? atoi(e) : 0; }();
+  p.trace = trace;
+  if (trace)
+    fprintf(stderr, "[gemm2] M=%d N=%d K=%d cg=%d bn=%d stages=%d groups=%d streamk=%d tiles=%dx%d\n", d->M, d->N, d->K, pl.cg,
+            pl.bn, p.stages, pl.groups, pl.streamk, pl.tiles_m, pl.tiles_n);
+
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  const long long a_rows = p.a_mn ? d->K : d->M, a_cols = p.a_mn ? d->M : d->K;
+  const long long b_rows = p.b_mn ? d->K : d->N, b_cols = p.b_mn ? d->N : d->K;
+  const int a_box = p.a_mn ? G2_BK : G2_BM, b_box = p.b_mn ? G2_BK : p.bn / pl.cg;
+  if ((rc = make_tensor_map(&ta_hi, d->a_hi, a_rows, a_cols, d->lda, a_box))) return rc;
+  if ((rc = make_tensor_map(&tb_hi, d->b_hi, b_rows, b_cols, d->ldb, b_box))) return rc;
+  if (d->nterms == 3) {
+    if ((rc = make_tensor_map(&ta_lo, d->a_lo, a_rows, a_cols, d->lda, a_box))) return rc;
+    if ((rc = make_tensor_map(&tb_lo, d->b_lo, b_rows, b_cols, d->ldb, b_box))) return rc;
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+  if (p.stats_mode == 3) {
+    cudaError_t e = cudaMemsetAsync(d->colstats, 0, sizeof(float) * d->N, stream);
+    if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "colsum memset: %s", cudaGetErrorString(e));
+  }
+  if (p.streamk) {
+    cudaError_t e = cudaMemset2DAsync(d->C, d->ldc * sizeof(float), 0, d->N * sizeof(float), d->M, stream);
+    if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "stream-K memset: %s", cudaGetErrorString(e));
+  }
+  const int nplanes = d->nterms == 3 ? 2 : 1;
+  const int stage_bytes = nplanes * (G2_BM * G2_BK * 2 + (p.bn / pl.cg) * G2_BK * 2);
+  const int smem_bytes = p.stages * stage_bytes + G2_STG_BYTES + 1024;
+  cudaError_t e = pl.cg == 2 ? launch_gemm2<2>(ta_hi, ta_lo, tb_hi, tb_lo, p, pl.groups, smem_bytes, stream)
+                             : launch_gemm2<1>(ta_hi, ta_lo, tb_hi, tb_lo, p, pl.groups, smem_bytes, stream);
+  if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "gemm2 launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+}  // namespace fxn
+
+// Debug: clock64 stamps of CTA 0 and CTA 1 of the last traced launch (FXN_GEMM_TRACE=1), relative to each CTA's start.
+extern "C" int fxn_debug_gemm_trace(long long* out32) {
+  long long h[2][16];
+  cudaError_t e = cudaMemcpyFromSymbol(h, fxn::g2_trace, sizeof(h));
+  if (e != cudaSuccess) return fxn::set_error(FXN_ERR_CUDA, "trace copy: %s", cudaGetErrorString(e));
+  for (int c = 0; c < 2; ++c)
+    for (int i = 0; i < 16; ++i) out32[c * 16 + i] = h[c][i] ? h[c][i] - h[c][0] : -1;
+  return 0;
+}

@@ -83,6 +83,9 @@ typedef struct fxn_gemm_desc {
   float stats_alpha; const float* stats_alpha_dev;
 } fxn_gemm_desc;
 int fxn_gemm(const fxn_gemm_desc* d, void* stream);
+/* Debug aid: with FXN_GEMM_TRACE=1 in the environment the persistent kernel stamps clock64 at its pipeline milestones
+ * for CTA 0 and CTA 1; this copies the 2 x 16 stamps (cycles since CTA start, -1 = not reached) of the last launch. */
+int fxn_debug_gemm_trace(long long* out32);
 int fxn_gemm_stat_tiles(int M);
 
 /* ---- BatchNorm1d (+ activation + dropout) ----

@@ -164,6 +164,14 @@ static int run_case(const Case& c, bool verbose) {
   return ok ? 0 : 1;
 }
 
+__global__ void fill_bf16_kernel(__nv_bfloat16* p, long long n, unsigned seed, float scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned x = (unsigned)i * 2654435761u ^ seed;
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    p[i] = __float2bfloat16(((x >> 8) * (1.0f / 8388608.0f) - 1.0f) * scale);
+  }
+}
+
 static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn, int nterms, int block_n, int splitk) {
   const long long a_rows = a_mn ? K : M, a_cols = a_mn ? M : K;
   const long long b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
@@ -173,8 +181,9 @@ static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn
   CK(cudaMalloc(&Ah, a_rows * lda * 2)); CK(cudaMalloc(&Al, a_rows * lda * 2));
   CK(cudaMalloc(&Bh, b_rows * ldb * 2)); CK(cudaMalloc(&Bl, b_rows * ldb * 2));
   CK(cudaMalloc(&C, (long long)M * N * 4));
-  CK(cudaMemset(Ah, 0, a_rows * lda * 2)); CK(cudaMemset(Al, 0, a_rows * lda * 2));
-  CK(cudaMemset(Bh, 0, b_rows * ldb * 2)); CK(cudaMemset(Bl, 0, b_rows * ldb * 2));
+  // random operands: all-zero inputs draw less power and flatter the clocks
+  fill_bf16_kernel<<<1024, 256>>>(Ah, a_rows * lda, 1u, 1.0f); fill_bf16_kernel<<<1024, 256>>>(Al, a_rows * lda, 2u, 0.004f);
+  fill_bf16_kernel<<<1024, 256>>>(Bh, b_rows * ldb, 3u, 1.0f); fill_bf16_kernel<<<1024, 256>>>(Bl, b_rows * ldb, 4u, 0.004f);
   fxn_gemm_desc d;
   memset(&d, 0, sizeof(d));
   d.M = M; d.N = N; d.K = K;
@@ -196,6 +205,15 @@ static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn
   double tf = 2.0 * M * N * K / (us * 1e-6) / 1e12;
   printf("BENCH %-28s M=%d N=%d K=%d terms=%d bn=%d splitk=%d : %.1f us  %.1f TFLOP/s algorithmic (%.1f issued)\n", name, M, N,
          K, nterms, block_n, splitk, us, tf, tf * nterms);
+  if (getenv("FXN_GEMM_TRACE")) {
+    long long t[32];
+    if (fxn_debug_gemm_trace(t) == 0) {
+      const char* names[11] = {"start", "setup done", "first load issued (last seg)", "all loads issued", "first stage landed",
+                               "first tile MMAs issued", "all MMAs issued", "first accumulator ready", "first tile stored",
+                               "all tiles stored", "end"};
+      for (int i = 0; i < 11; ++i) printf("  trace %-30s cta0 %8lld  cta1 %8lld cycles\n", names[i], t[i], t[16 + i]);
+    }
+  }
   cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl); cudaFree(C);
 }
 
@@ -205,6 +223,11 @@ int main(int argc, char** argv) {
   CK(cudaGetDeviceProperties(&prop, dev));
   printf("device: %s sm_%d%d, %d SMs, lib version %d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount,
          fxn_version());
+  if (argc >= 10 && !strcmp(argv[1], "one")) {   // one M N K a_mn b_mn nterms bn splitk : time a single shape (for ncu)
+    bench_case("one", atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]),
+               atoi(argv[9]));
+    return 0;
+  }
   std::vector<Case> cases = {
       // M, N, K, a_mn, b_mn, terms, bias, splitk, stats, planes, block_n
       {128, 128, 64, 0, 0, 1, 0, 1, 0, 0, 0},      // smallest K-major, single term
@@ -225,6 +248,13 @@ int main(int argc, char** argv) {
       {1024, 512, 5000, 0, 0, 3, 1, 1, 1, 0, 128}, // same with 128-wide tiles
       {512, 5000, 1024, 1, 1, 3, 0, 1, 0, 0, 0},   // config 2 wgrad (K reduced)
       {1024, 256, 512, 0, 0, 1, 1, 1, 0, 0, 0},    // single-term mode
+      {4096, 2048, 128, 0, 0, 3, 1, 1, 1, 1, 0},   // more tiles than CTA groups: persistent loop + TMEM double buffer
+      {333, 2500, 96, 0, 1, 3, 1, 1, 0, 1, 0},     // ragged rows inside a CTA pair, many column tiles, tiny K
+      {3000, 96, 200, 0, 0, 3, 1, 1, 1, 1, 0},     // narrow N, partial last pair
+      {512, 5000, 4096, 1, 1, 3, 0, -1, 0, 0, 0},  // stream-K wgrad
+      {307, 3000, 1000, 1, 1, 3, 1, -1, 0, 0, 0},  // stream-K, ragged, with bias
+      {4096, 128, 8000, 0, 0, 3, 1, -1, 0, 0, 0},  // stream-K, K-major, long K
+      {100, 1000, 4096, 1, 1, 3, 0, -1, 0, 0, 0},  // single-CTA groups (M <= 128) with stream-K
   };
   int fails = 0;
   for (const Case& c : cases) fails += run_case(c, true);
@@ -234,6 +264,13 @@ int main(int argc, char** argv) {
     bench_case("cfg2 enc0 fwd bn128", 4096, 512, 5000, 0, 0, 3, 128, 1);
     bench_case("cfg2 enc0 fwd splitk2", 4096, 512, 5000, 0, 0, 3, 256, 2);
     bench_case("cfg2 enc0 fwd 1-term", 4096, 512, 5000, 0, 0, 1, 256, 1);
+    bench_case("cfg2 enc0 fwd auto", 4096, 512, 5000, 0, 0, 3, 0, 0);
+    bench_case("cfg2 enc0 wgrad auto", 512, 5000, 4096, 1, 1, 3, 0, -1);
+    bench_case("cfg2 enc1 wgrad auto", 307, 3000, 4096, 1, 1, 3, 0, -1);
+    bench_case("cfg2 dgrad h<-latent", 4096, 512, 256, 0, 1, 3, 0, 0);
+    bench_case("cfg3 decoder out", 4096, 5000, 512, 0, 0, 3, 0, 0);
+    bench_case("cfg4 fc dgrad", 4096, 64000, 128, 0, 1, 3, 0, 0);
+    bench_case("cfg5 enc wgrad auto", 1024, 24000, 4096, 1, 1, 3, 0, -1);
     bench_case("cfg2 enc0 wgrad", 512, 5000, 4096, 1, 1, 3, 256, 1);
     bench_case("cfg2 enc0 wgrad bn128", 512, 5000, 4096, 1, 1, 3, 128, 1);
     bench_case("cfg2 enc1 fwd", 4096, 307, 3000, 0, 0, 3, 0, 1);
