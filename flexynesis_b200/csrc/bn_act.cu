@@ -36,6 +36,11 @@ __device__ __forceinline__ float act_grad(float y, int act) {
   }
 }
 
+// Narrow, contiguous matrices (flexGCN normalises [B*N x 32]) are processed as [rows / fold x 64] so that all 256 threads
+// of a block carry data; column c of the folded view belongs to channel c % period. The Philox element index is
+// unchanged by the fold (r * cols / 8 + c / 8 is the same number in both views).
+__device__ __forceinline__ int chan(int c, int period) { return period ? c % period : c; }
+
 struct BnArgs {
   const float* V; long long ldv;     // input of the norm [rows x cols]
   long long rows; int cols;
@@ -52,6 +57,9 @@ struct BnArgs {
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ldp;
   float* saved;           // [2][cols]: mean, rstd
   int rpb;                // rows per block (multiple of 32)
+  long long stat_rows;    // rows the statistics are taken over (= rows * fold)
+  int pcols;              // number of real channels: the per-channel vectors have this length
+  int period;             // 0, or pcols when `fold` consecutive rows of a contiguous narrow matrix are viewed as one row
 };
 
 constexpr int BN_COLS = 64;     // columns per block (8 per thread x 8 threads)
@@ -96,22 +104,23 @@ __global__ void __launch_bounds__(BN_THREADS) bn_fwd_kernel(const BnArgs a) {
     const int col = threadIdx.x & (BN_COLS - 1), lane4 = threadIdx.x >> 6;
     const int c = c0 + col;
     const bool ok = c < a.cols;
+    const int pc = chan(c, a.period);
     if (a.train) {
       float part = 0.f;
       if (ok)
-        for (int t = lane4; t < a.ntiles; t += 4) part += a.partials[(static_cast<long long>(t) * 2) * a.pld + c];
+        for (int t = lane4; t < a.ntiles; t += 4) part += a.partials[(static_cast<long long>(t) * 2) * a.pld + pc];
       s_red[lane4][col] = part;
       __syncthreads();
-      if (lane4 == 0) s_mean[col] = (s_red[0][col] + s_red[1][col] + s_red[2][col] + s_red[3][col]) / static_cast<float>(a.rows);
+      if (lane4 == 0) s_mean[col] = (s_red[0][col] + s_red[1][col] + s_red[2][col] + s_red[3][col]) / static_cast<float>(a.stat_rows);
       __syncthreads();
       const float mean = s_mean[col];
       float m2 = 0.f;
       if (ok)
         for (int t = lane4; t < a.ntiles; t += 4) {
           const long long r0 = static_cast<long long>(t) * a.tile_rows;
-          const float n = static_cast<float>(min(static_cast<long long>(a.tile_rows), a.rows - r0));
-          const float d = a.partials[(static_cast<long long>(t) * 2) * a.pld + c] / n - mean;
-          m2 += a.partials[(static_cast<long long>(t) * 2 + 1) * a.pld + c] + n * d * d;
+          const float n = static_cast<float>(min(static_cast<long long>(a.tile_rows), a.stat_rows - r0));
+          const float d = a.partials[(static_cast<long long>(t) * 2) * a.pld + pc] / n - mean;
+          m2 += a.partials[(static_cast<long long>(t) * 2 + 1) * a.pld + pc] + n * d * d;
         }
       __syncthreads();
       s_red[lane4][col] = m2;
@@ -123,20 +132,20 @@ __global__ void __launch_bounds__(BN_THREADS) bn_fwd_kernel(const BnArgs a) {
         float mean, var;
         if (a.train) {
           mean = s_mean[col];
-          var = (s_red[0][col] + s_red[1][col] + s_red[2][col] + s_red[3][col]) / static_cast<float>(a.rows);
+          var = (s_red[0][col] + s_red[1][col] + s_red[2][col] + s_red[3][col]) / static_cast<float>(a.stat_rows);
         } else {
-          mean = a.running_mean[c];
-          var = a.running_var[c];
+          mean = a.running_mean[pc];
+          var = a.running_var[pc];
         }
         const float rstd = rsqrtf(var + a.eps);
-        sc = a.gamma[c] * rstd;
-        sh = a.beta[c] - mean * sc;
-        if (a.train && blockIdx.y == 0) {
-          if (a.saved) { a.saved[c] = mean; a.saved[a.cols + c] = rstd; }
+        sc = a.gamma[pc] * rstd;
+        sh = a.beta[pc] - mean * sc;
+        if (a.train && blockIdx.y == 0 && c == pc) {      // one writer per channel (folded views repeat channels)
+          if (a.saved) { a.saved[pc] = mean; a.saved[a.pcols + pc] = rstd; }
           if (a.running_mean) {
-            const float n = static_cast<float>(a.rows);
-            a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * mean;
-            a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * var * n / (n - 1.f);
+            const float n = static_cast<float>(a.stat_rows);
+            a.running_mean[pc] = (1.f - a.momentum) * a.running_mean[pc] + a.momentum * mean;
+            a.running_var[pc] = (1.f - a.momentum) * a.running_var[pc] + a.momentum * var * n / (n - 1.f);
           }
         }
       }
@@ -229,6 +238,7 @@ struct BnBwdArgs {
   float grad_scale;                     // multiplies dOut (1 unless the caller folds a loss weight in)
   int acc_affine;                       // dgamma/dbeta += (module applied several times per step)
   int rpb;                              // rows per block (multiple of 32)
+  long long stat_rows; int pcols, period;   // see BnArgs
 };
 
 // recompute g = dOut * dropout * act'(y) for 8 columns of row r; also returns xhat
@@ -249,13 +259,28 @@ __device__ __forceinline__ void bn_bwd_load(const BnBwdArgs& a, long long r, int
                            static_cast<unsigned long long>(r) * ((a.cols + 7) / 8) + (c >> 3), a.p_drop);
     }
   }
+  float vv[8], gg[8];
+  const bool vec = (c + 8 <= a.cols) && (a.ldv % 4 == 0) && (a.ldg % 4 == 0) &&
+                   (((reinterpret_cast<uintptr_t>(a.V) | reinterpret_cast<uintptr_t>(a.dOut)) & 15) == 0);
+  if (vec) {
+    const float4 v0 = *reinterpret_cast<const float4*>(a.V + r * a.ldv + c), v1 = *reinterpret_cast<const float4*>(a.V + r * a.ldv + c + 4);
+    const float4 g0 = *reinterpret_cast<const float4*>(a.dOut + r * a.ldg + c), g1 = *reinterpret_cast<const float4*>(a.dOut + r * a.ldg + c + 4);
+    vv[0] = v0.x; vv[1] = v0.y; vv[2] = v0.z; vv[3] = v0.w; vv[4] = v1.x; vv[5] = v1.y; vv[6] = v1.z; vv[7] = v1.w;
+    gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      vv[j] = (c + j < a.cols) ? a.V[r * a.ldv + c + j] : 0.f;
+      gg[j] = (c + j < a.cols) ? a.dOut[r * a.ldg + c + j] : 0.f;
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (c + j < a.cols) {
-      const float v = a.V[r * a.ldv + c + j];
+      const float v = vv[j];
       const float xh = (v - s_mean[tc + j]) * s_rstd[tc + j];
       const float y = fmaf(xh, s_gamma[tc + j], s_beta[tc + j]);
-      float d = a.dOut[r * a.ldg + c + j] * a.grad_scale;
+      float d = gg[j] * a.grad_scale;
       d = ((keep >> j) & 1u) ? d * keep_scale : 0.f;
       g[j] = d * act_grad(y, a.act);
       xhat[j] = xh;
@@ -273,10 +298,11 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnBwdAr
   if (threadIdx.x < BN_COLS) {
     const int c = c0 + threadIdx.x;
     const bool ok = c < a.cols;
-    s_mean[threadIdx.x] = ok ? a.saved[c] : 0.f;
-    s_rstd[threadIdx.x] = ok ? a.saved[a.cols + c] : 0.f;
-    s_gamma[threadIdx.x] = ok ? a.gamma[c] : 0.f;
-    s_beta[threadIdx.x] = ok ? a.beta[c] : 0.f;
+    const int pc = chan(c, a.period);
+    s_mean[threadIdx.x] = ok ? a.saved[pc] : 0.f;
+    s_rstd[threadIdx.x] = ok ? a.saved[a.pcols + pc] : 0.f;
+    s_gamma[threadIdx.x] = ok ? a.gamma[pc] : 0.f;
+    s_beta[threadIdx.x] = ok ? a.beta[pc] : 0.f;
   }
   __syncthreads();
   const int tc = (threadIdx.x & 7) * 8;
@@ -304,7 +330,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnBwdAr
       float t = 0.f;
 #pragma unroll 8
       for (int i = 0; i < 32; ++i) t += s_acc[which][i][col];
-      atomicAdd(a.sums + static_cast<long long>(which) * a.cols + c0 + col, t);
+      atomicAdd(a.sums + static_cast<long long>(which) * a.pcols + chan(c0 + col, a.period), t);
     }
   }
 }
@@ -313,20 +339,21 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const BnBwdArg
   __shared__ float s_mean[BN_COLS], s_rstd[BN_COLS], s_gamma[BN_COLS], s_beta[BN_COLS], s_m1[BN_COLS], s_m2[BN_COLS];
   __shared__ float s_acc[32][BN_COLS + 1];
   const int c0 = blockIdx.x * BN_COLS;
-  const float inv_n = 1.f / static_cast<float>(a.rows);
+  const float inv_n = 1.f / static_cast<float>(a.stat_rows);
   if (threadIdx.x < BN_COLS) {
     const int c = c0 + threadIdx.x;
     const bool ok = c < a.cols;
-    s_mean[threadIdx.x] = ok ? a.saved[c] : 0.f;
-    s_rstd[threadIdx.x] = ok ? a.saved[a.cols + c] : 0.f;
-    s_gamma[threadIdx.x] = ok ? a.gamma[c] : 0.f;
-    s_beta[threadIdx.x] = ok ? a.beta[c] : 0.f;
-    const float sum_g = ok ? a.sums[c] : 0.f, sum_gx = ok ? a.sums[a.cols + c] : 0.f;
+    const int pc = chan(c, a.period);
+    s_mean[threadIdx.x] = ok ? a.saved[pc] : 0.f;
+    s_rstd[threadIdx.x] = ok ? a.saved[a.pcols + pc] : 0.f;
+    s_gamma[threadIdx.x] = ok ? a.gamma[pc] : 0.f;
+    s_beta[threadIdx.x] = ok ? a.beta[pc] : 0.f;
+    const float sum_g = ok ? a.sums[pc] : 0.f, sum_gx = ok ? a.sums[a.pcols + pc] : 0.f;
     s_m1[threadIdx.x] = sum_g * inv_n;
     s_m2[threadIdx.x] = sum_gx * inv_n;
-    if (ok && blockIdx.y == 0) {
-      if (a.dbeta) a.dbeta[c] = (a.acc_affine ? a.dbeta[c] : 0.f) + sum_g;
-      if (a.dgamma) a.dgamma[c] = (a.acc_affine ? a.dgamma[c] : 0.f) + sum_gx;
+    if (ok && blockIdx.y == 0 && c == pc) {
+      if (a.dbeta) a.dbeta[pc] = (a.acc_affine ? a.dbeta[pc] : 0.f) + sum_g;
+      if (a.dgamma) a.dgamma[pc] = (a.acc_affine ? a.dgamma[pc] : 0.f) + sum_gx;
     }
   }
   __syncthreads();
@@ -351,9 +378,14 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const BnBwdArg
         sb[j] += dz[j];
       }
       if (a.dV) {
+        if ((c + 8 <= a.cols) && (a.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.dV) & 15) == 0)) {
+          *reinterpret_cast<float4*>(a.dV + r * a.ldd + c) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+          *reinterpret_cast<float4*>(a.dV + r * a.ldd + c + 4) = make_float4(dz[4], dz[5], dz[6], dz[7]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (c + j < a.cols) a.dV[r * a.ldd + c + j] = dz[j];
+          for (int j = 0; j < 8; ++j)
+            if (c + j < a.cols) a.dV[r * a.ldd + c + j] = dz[j];
+        }
       }
       if (a.dv_hi && c < pcols) {
         __align__(16) __nv_bfloat16 h[8];
@@ -373,7 +405,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const BnBwdArg
       float t = 0.f;
 #pragma unroll 8
       for (int i = 0; i < 32; ++i) t += s_acc[i][threadIdx.x];
-      atomicAdd(a.dbias + c0 + threadIdx.x, t);
+      atomicAdd(a.dbias + chan(c0 + threadIdx.x, a.period), t);
     }
   }
 }
@@ -437,6 +469,17 @@ extern "C" int fxn_bn_act_fwd(const fxn_bn_fwd_desc* d, void* stream_) {
   a.out = d->out; a.ldo = d->ldo;
   a.out_hi = static_cast<__nv_bfloat16*>(d->out_hi); a.out_lo = static_cast<__nv_bfloat16*>(d->out_lo); a.ldp = d->ldp;
   a.saved = d->saved;
+  a.stat_rows = a.rows; a.pcols = a.cols; a.period = 0;
+  {
+    // fold narrow contiguous matrices into 64-wide rows (see chan())
+    const int f = (a.cols == 8 || a.cols == 16 || a.cols == 32) ? 64 / a.cols : 1;
+    const bool contiguous = a.ldv == a.cols && (!a.out || a.ldo == a.cols) && (!a.out_hi || a.ldp == a.cols) &&
+                            (!a.mask || a.ldm == a.cols);
+    if (f > 1 && contiguous && a.rows % f == 0 && a.rows >= 4096) {
+      a.period = a.cols; a.rows /= f; a.cols = 64;
+      a.ldv = 64; a.ldo = 64; a.ldp = 64; a.ldm = 64;
+    }
+  }
   const int width = a.out_hi ? ((a.cols + 7) & ~7) : a.cols;
   a.rpb = bn_rows_per_block(a.rows, ceil_div(width, BN_COLS));
   dim3 grid(ceil_div(width, BN_COLS), ceil_div(a.rows, a.rpb));
@@ -460,8 +503,18 @@ extern "C" int fxn_bn_act_bwd(const fxn_bn_bwd_desc* d, void* stream_) {
   a.dv_hi = static_cast<__nv_bfloat16*>(d->dv_hi); a.dv_lo = static_cast<__nv_bfloat16*>(d->dv_lo); a.ldp = d->ldp;
   a.grad_scale = d->grad_scale == 0.f ? 1.f : d->grad_scale;
   a.acc_affine = d->accumulate_affine;
-  cudaError_t e = cudaMemsetAsync(a.sums, 0, sizeof(float) * 2 * a.cols, stream);
-  if (e == cudaSuccess && a.dbias) e = cudaMemsetAsync(a.dbias, 0, sizeof(float) * a.cols, stream);
+  a.stat_rows = a.rows; a.pcols = a.cols; a.period = 0;
+  {
+    const int f = (a.cols == 8 || a.cols == 16 || a.cols == 32) ? 64 / a.cols : 1;
+    const bool contiguous = a.ldv == a.cols && a.ldg == a.cols && (!a.dV || a.ldd == a.cols) &&
+                            (!a.dv_hi || a.ldp == a.cols) && (!a.mask || a.ldm == a.cols);
+    if (f > 1 && contiguous && a.rows % f == 0 && a.rows >= 4096) {
+      a.period = a.cols; a.rows /= f; a.cols = 64;
+      a.ldv = 64; a.ldg = 64; a.ldd = 64; a.ldp = 64; a.ldm = 64;
+    }
+  }
+  cudaError_t e = cudaMemsetAsync(a.sums, 0, sizeof(float) * 2 * a.pcols, stream);
+  if (e == cudaSuccess && a.dbias) e = cudaMemsetAsync(a.dbias, 0, sizeof(float) * a.pcols, stream);
   if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "bn_bwd memset: %s", cudaGetErrorString(e));
   const int width = a.dv_hi ? ((a.cols + 7) & ~7) : a.cols;
   a.rpb = bn_rows_per_block(a.rows, ceil_div(width, BN_COLS));
