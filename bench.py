@@ -359,7 +359,7 @@ def run_b200(args, w):
     import torch.distributed as dist
     from flexynesis_b200 import _lib as L
     from flexynesis_b200.fit import GraphedStep
-    from flexynesis_b200.parallel import GradAllReduce
+    from flexynesis_b200.parallel import GradAllReduce, NvlsDataParallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -370,12 +370,32 @@ def run_b200(args, w):
         dist.init_process_group("nccl", device_id=dev)
     B = w["B"]
     prob = build_problem(w, rank)                      # this rank's shard of the sample-sharded dataset
-    model = build_model(w, prob, dev)
+    dp_mode, dp_note = "single", ""
+    if world > 1 and not args.nccl and NvlsDataParallel.available():
+        # arenas in symmetric memory; gradient reduce-scatter / Adam / parameter all-gather through NVSwitch multicast
+        with NvlsDataParallel.arena_allocation():
+            model = build_model(w, prob, dev)
+            eng = model.engine(dev)
+        try:
+            allreduce = NvlsDataParallel(eng)
+            ok = 1
+        except Exception as e:                         # no multicast support on this box: say so, use NCCL
+            allreduce, ok, dp_note = None, 0, f"NVLS unavailable ({type(e).__name__}: {e})"[:200]
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 1:
+            dp_mode = "nvls"
+        else:
+            allreduce, dp_mode = GradAllReduce(world), "nccl"
+    else:
+        model = build_model(w, prob, dev)
+        allreduce = GradAllReduce(world) if world > 1 else None
+        dp_mode = "nccl" if world > 1 else "single"
+    model.engine(dev).seed += 7919 * rank              # different dropout streams on different shards
     nparams = sum(p.numel() for p in model.parameters())
 
     # ---------------- resident-input arm (value) ----------------
     batch = device_batch(prob, dev)
-    allreduce = GradAllReduce(world) if world > 1 else None
     step = GraphedStep(model, batch, allreduce=allreduce, grad_scale=1.0 / world)
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -467,8 +487,12 @@ def run_b200(args, w):
                                     "the 126 MB L2; the roofline kernel is timed with an explicit 256 MB L2 flush",
                        "input_prep": "value: planes of the resident full batch are split once and reused; e2e: re-split "
                                      "every step inside the captured graph",
-                       "step": "CUDA-graph replay of fwd+bwd+clip+Adam+plane refresh"
-                               + ("; NCCL all-reduce of the flat gradient arena between the two graphs" if world > 1 else "")},
+                       "step": "CUDA-graph replay of fwd+bwd+clip+Adam+plane refresh" + {
+                           "single": "",
+                           "nccl": "; NCCL all-reduce of the flat gradient arena between the backward and optimizer graphs",
+                           "nvls": "; gradients reduce-scattered by multimem.ld_reduce, Adam on a 1/W slice per rank, "
+                                   "parameters all-gathered by multimem.st (NVSwitch multicast, csrc/dp.cu)"}[dp_mode],
+                       "data_parallel": dp_mode, "data_parallel_note": dp_note},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
             "gpu_launches": launches, "launches_per_step": step.launches_per_step,
@@ -489,6 +513,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl", action="store_true", help="multi-GPU: NCCL all-reduce instead of the NVSwitch multicast step")
     ap.add_argument("--profile", action="store_true", help="timed steps only (for ncu launch lists): no e2e/roofline/cpu legs")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

@@ -86,7 +86,7 @@ SYMBOLS = [
     "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
     "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn", "fxn_gcn_fwd", "fxn_gcn_bwd",
-    "fxn_merge_col_stats", "fxn_debug_gemm_trace",
+    "fxn_merge_col_stats", "fxn_debug_gemm_trace", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast",
 ]
 
 
@@ -332,3 +332,17 @@ def gcn_bwd(X, dO, B, N, Fin, emb, csr_in, csr_out, W, dW, dbias, dX) -> None:
 def merge_col_stats(partials, ntiles, tile_rows, rows, cols, pld, merged) -> None:
     check(lib.fxn_merge_col_stats(C.c_void_p(partials), C.c_int(ntiles), C.c_int(tile_rows), c_ll(rows), C.c_int(cols),
                                   C.c_int(pld), C.c_void_p(merged), C.c_void_p(stream())), "fxn_merge_col_stats")
+
+
+def dp_reduce_sumsq(mc_grad, grad_local, begin, end, scale, mc_partials, rank, scratch16, step) -> None:
+    check(lib.fxn_dp_reduce_sumsq(C.c_void_p(mc_grad), C.c_void_p(grad_local), c_ll(begin), c_ll(end), C.c_float(scale),
+                                  C.c_void_p(mc_partials), C.c_int(rank), C.c_void_p(scratch16), C.c_void_p(step),
+                                  C.c_void_p(stream())), "fxn_dp_reduce_sumsq")
+
+
+def dp_adam_bcast(mc_param, param_local, grad_local, m, v, begin, end, partials, world, lr, max_norm, step, norm_out,
+                  beta1=0.9, beta2=0.999, eps=1e-8) -> None:
+    check(lib.fxn_dp_adam_bcast(C.c_void_p(mc_param), C.c_void_p(param_local), C.c_void_p(grad_local), C.c_void_p(m),
+                                C.c_void_p(v), c_ll(begin), c_ll(end), C.c_void_p(partials), C.c_int(world), C.c_float(lr),
+                                C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(max_norm), C.c_void_p(step),
+                                C.c_void_p(norm_out), C.c_void_p(stream())), "fxn_dp_adam_bcast")

@@ -1,0 +1,161 @@
+// Data-parallel step fused with the NVSwitch collectives (NVLink SHARP / "NVLS" multicast objects).
+//
+// The reference has no multi-GPU path (pl.Trainer(devices=1), flexynesis/main.py:223). The plain port of DDP is
+// "all-reduce the gradient arena with NCCL, then run clip + Adam on every rank" -- W ranks each read and write the whole
+// model. Here the parameter and gradient arenas of every rank are mapped behind ONE multicast address (torch symmetric
+// memory), the arena is cut into W slices, and rank r
+//   1. pulls slice r of the SUMMED gradient with multimem.ld_reduce (the switch adds the W copies in flight: one load
+//      instruction replaces a reduce-scatter), scales it by 1/W, keeps it, and accumulates its squared norm;
+//   2. publishes that partial norm into slot r of every rank with one multimem.st;
+//   -- system-wide barrier --
+//   3. clips with the global norm, runs Adam on slice r only (moments exist for the slice only), and stores the new
+//      parameters with multimem.st, which lands in every rank's parameter arena (one store replaces an all-gather).
+// Per step and GPU: P/W elements in through the switch, P/W out, instead of 2 P (W-1)/W for a ring all-reduce, and the
+// optimizer touches P/W instead of P elements.
+#include "fxn_internal.h"
+#include "ptx.cuh"
+
+namespace fxn {
+
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc_addr) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc_addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc_addr, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void multimem_st_scalar(float* mc_addr, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+}
+
+// grad_local[i] = scale * sum_ranks grad[i] for i in [begin, end) (multiples of 4); slot `rank` of the symmetric partial
+// array receives the squared norm of that slice on every rank. scratch: {double sum, unsigned arrivals}, zero on entry and
+// left zero on exit.
+__global__ void __launch_bounds__(256)
+dp_reduce_kernel(const float* __restrict__ mc_grad, float* __restrict__ grad_local, long long begin, long long end,
+                 float scale, float* __restrict__ mc_partials, int rank, double* __restrict__ scratch_sum,
+                 unsigned* __restrict__ scratch_count) {
+  __shared__ double s_part[8];
+  double acc = 0.0;
+  const long long n4 = (end - begin) / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long off = begin + 4 * i;
+    float4 g = multimem_ld_reduce_add(mc_grad + off);
+    g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
+    *reinterpret_cast<float4*>(grad_local + off) = g;
+    acc += static_cast<double>(g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    atomicAdd(scratch_sum, t);
+    __threadfence();
+    const unsigned arrived = atomicAdd(scratch_count, 1u) + 1u;
+    if (arrived == gridDim.x) {                       // last block: publish this rank's partial to every rank
+      __threadfence();
+      const double total = *reinterpret_cast<volatile double*>(scratch_sum);
+      multimem_st_scalar(mc_partials + rank, static_cast<float>(total));
+      *scratch_sum = 0.0;
+      *scratch_count = 0u;
+      __threadfence_system();
+    }
+  }
+}
+
+// clip_grad_norm_(max_norm) with the global norm assembled from the W partials, Adam on [begin, end), new parameters
+// multicast into every rank's arena. exp_avg / exp_avg_sq are indexed like the arena (only the slice is touched).
+__global__ void __launch_bounds__(256)
+dp_adam_bcast_kernel(float* __restrict__ mc_param, const float* __restrict__ param_local, const float* __restrict__ grad_local,
+                     float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, long long begin, long long end,
+                     const float* __restrict__ partials, int world, float lr, float beta1, float beta2, float eps,
+                     float max_norm, const long long* __restrict__ step, float* __restrict__ norm_out) {
+  float total = 0.f;
+  for (int r = 0; r < world; ++r) total += partials[r];
+  const float norm = sqrtf(total);
+  const float coef = max_norm > 0.f ? fminf(max_norm / (norm + 1e-6f), 1.f) : 1.f;
+  if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
+  // same arithmetic as clip_adam_kernel (optim.cu); *step was incremented by fxn_dp_reduce_sumsq of this step
+  const double t = static_cast<double>(*step);
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), t));
+  const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), t));
+  const float step_size = lr / bc1;
+  const float bc2_sqrt = sqrtf(bc2);
+  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  const long long n4 = (end - begin) / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long off = begin + 4 * i;
+    const float4 g4 = *reinterpret_cast<const float4*>(grad_local + off);
+    float4 m4 = *reinterpret_cast<const float4*>(exp_avg + off);
+    float4 v4 = *reinterpret_cast<const float4*>(exp_avg_sq + off);
+    float4 p4 = *reinterpret_cast<const float4*>(param_local + off);
+    const float g[4] = {g4.x * coef, g4.y * coef, g4.z * coef, g4.w * coef};
+    float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w}, p[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      m[j] = m[j] + (g[j] - m[j]) * omb1;
+      v[j] = v[j] * beta2 + omb2 * g[j] * g[j];
+      p[j] = p[j] - step_size * (m[j] / (sqrtf(v[j]) / bc2_sqrt + eps));
+    }
+    *reinterpret_cast<float4*>(exp_avg + off) = make_float4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<float4*>(exp_avg_sq + off) = make_float4(v[0], v[1], v[2], v[3]);
+    multimem_st(mc_param + off, make_float4(p[0], p[1], p[2], p[3]));
+  }
+}
+
+__global__ void dp_step_inc_kernel(long long* step) { *step += 1; }
+
+}  // namespace fxn
+
+using namespace fxn;
+
+extern "C" int fxn_dp_reduce_sumsq(const void* mc_grad, float* grad_local, long long begin, long long end, float scale,
+                                   void* mc_partials, int rank, void* scratch16, long long* step_counter, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!mc_grad || !grad_local || !mc_partials || !scratch16) return set_error(FXN_ERR_ARG, "fxn_dp_reduce_sumsq: null argument");
+  if (begin % 4 || end % 4 || end < begin || (reinterpret_cast<uintptr_t>(mc_grad) & 15) || (reinterpret_cast<uintptr_t>(grad_local) & 15))
+    return set_error(FXN_ERR_ARG, "fxn_dp_reduce_sumsq: slice bounds and bases must be 16-byte aligned");
+  if (step_counter) {
+    dp_step_inc_kernel<<<1, 1, 0, stream>>>(step_counter);
+    FXN_CHECK_LAUNCH("dp_step_inc");
+  }
+  long long n4 = (end - begin) / 4;
+  int blocks = static_cast<int>((n4 + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  dp_reduce_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(mc_grad), grad_local, begin, end, scale,
+                                               static_cast<float*>(mc_partials), rank, static_cast<double*>(scratch16),
+                                               reinterpret_cast<unsigned*>(static_cast<char*>(scratch16) + 8));
+  FXN_CHECK_LAUNCH("dp_reduce");
+  return 0;
+}
+
+extern "C" int fxn_dp_adam_bcast(void* mc_param, const float* param_local, const float* grad_local, float* exp_avg,
+                                 float* exp_avg_sq, long long begin, long long end, const float* partials, int world, float lr,
+                                 float beta1, float beta2, float eps, float max_norm, const long long* step_counter,
+                                 float* norm_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!mc_param || !param_local || !grad_local || !exp_avg || !exp_avg_sq || !partials || !step_counter)
+    return set_error(FXN_ERR_ARG, "fxn_dp_adam_bcast: null argument");
+  if (begin % 4 || end % 4 || end < begin) return set_error(FXN_ERR_ARG, "fxn_dp_adam_bcast: slice bounds must be multiples of 4");
+  long long n4 = (end - begin) / 4;
+  int blocks = static_cast<int>((n4 + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  dp_adam_bcast_kernel<<<blocks, 256, 0, stream>>>(static_cast<float*>(mc_param), param_local, grad_local, exp_avg, exp_avg_sq,
+                                                   begin, end, partials, world, lr, beta1, beta2, eps, max_norm, step_counter,
+                                                   norm_out);
+  FXN_CHECK_LAUNCH("dp_adam_bcast");
+  return 0;
+}

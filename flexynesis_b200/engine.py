@@ -29,6 +29,8 @@ def pad128(n: int) -> int:
 class ParamArena:
     """Re-homes the parameters of `module` into one flat fp32 buffer; grads / exp_avg / exp_avg_sq mirror it."""
 
+    allocator = None        # optional callable(numel, device) -> zeroed fp32 tensor (see parallel.NvlsDataParallel)
+
     def __init__(self, module: nn.Module, device: torch.device):
         self.device = device
         self.names: List[str] = []
@@ -44,10 +46,11 @@ class ParamArena:
             self.shape[name] = p.shape
             self.params[name] = p
             off += pad8(p.numel())
-        self.numel = off
-        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
-        self.grad = torch.zeros_like(self.flat)
-        self.exp_avg = torch.zeros_like(self.flat)
+        self.numel = (off + 255) // 256 * 256                  # any world size <= 64 cuts it into 16-byte aligned slices
+        alloc = ParamArena.allocator                           # data-parallel runs place the arenas in symmetric memory
+        self.flat = alloc(self.numel, device) if alloc else torch.zeros(self.numel, dtype=torch.float32, device=device)
+        self.grad = alloc(self.numel, device) if alloc else torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros(self.numel, dtype=torch.float32, device=device)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step = torch.zeros(1, dtype=torch.int64, device=device)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=device)

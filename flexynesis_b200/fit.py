@@ -33,7 +33,12 @@ class GraphedStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self.ws = model.fit_step(batch, lr=lr, allreduce=allreduce, grad_scale=grad_scale)
+                if hasattr(allreduce, "step"):
+                    g, y = model._split_batch(batch)
+                    self.ws = eng.forward_backward(g, y, None)
+                    allreduce.step(lr)
+                else:
+                    self.ws = model.fit_step(batch, lr=lr, allreduce=allreduce, grad_scale=grad_scale)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         n0 = L.launch_count()
@@ -42,19 +47,25 @@ class GraphedStep:
             with torch.cuda.graph(self.g1):
                 self.ws = model.fit_step(batch, lr=lr, grad_scale=grad_scale)
         else:
-            self.g1, self.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            self.g1, self.g2 = torch.cuda.CUDAGraph(), None
             with torch.cuda.graph(self.g1):
                 g, y = model._split_batch(batch)
                 self.ws = eng.forward_backward(g, y, None)
-            with torch.cuda.graph(self.g2):
-                eng.optimizer_step(lr, 1.0, grad_scale)
-        self.launches_per_step = L.launch_count() - n0
+            if not hasattr(allreduce, "step"):             # NCCL all-reduce + the single-GPU optimizer kernel
+                self.g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.g2):
+                    eng.optimizer_step(lr, 1.0, grad_scale)
+        self.lr = lr
+        self.launches_per_step = L.launch_count() - n0 + (3 if self.g2 is None and allreduce is not None else 0)
 
     def __call__(self):
         self.g1.replay()
-        if self.g2 is not None:
-            self.allreduce(self.eng.arena.grad)
-            self.g2.replay()
+        if self.allreduce is not None:
+            if self.g2 is not None:
+                self.allreduce(self.eng.arena.grad)
+                self.g2.replay()
+            else:
+                self.allreduce.step(self.lr)               # NvlsDataParallel: fused reduce-scatter / Adam / all-gather
         return self.ws
 
     def losses(self) -> Dict[str, torch.Tensor]:

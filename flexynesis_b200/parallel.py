@@ -72,3 +72,86 @@ def broadcast_parameters(arena_flat: torch.Tensor, buffers: Dict[str, torch.Tens
     for b in buffers.values():
         if b.dtype.is_floating_point or b.dtype in (torch.int64, torch.int32):
             dist.broadcast(b, src, group=group)
+
+
+class NvlsDataParallel:
+    """Data-parallel optimizer step over NVSwitch multicast (csrc/dp.cu): the gradient arena is reduce-scattered by
+    `multimem.ld_reduce` (in-switch sum), each rank clips with the global norm and runs Adam on its 1/W slice only, and
+    the updated parameters are all-gathered by `multimem.st`. Needs torch symmetric memory with multicast support
+    (NVLS: every GPU behind one NVSwitch domain); `available()` says whether this process group has it -- callers fall
+    back to GradAllReduce (NCCL) + the single-GPU optimizer kernel and SAY SO in their report.
+
+    Usage:  with NvlsDataParallel.arena_allocation(): eng = model.engine(dev)     # arenas land in symmetric memory
+            dp = NvlsDataParallel(eng)                                               # rendezvous (collective)
+            ...backward...; dp.step(lr)                                              # collective
+    """
+
+    _pending = []          # tensors handed out by the allocator, rendezvoused by the next constructor
+
+    @staticmethod
+    def available() -> bool:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+        except Exception:
+            return False
+        return dist.is_initialized() and dist.get_world_size() > 1 and torch.cuda.is_available()
+
+    @staticmethod
+    def _alloc(numel, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        t.zero_()
+        NvlsDataParallel._pending.append(t)
+        return t
+
+    class arena_allocation:
+        def __enter__(self):
+            from .engine import ParamArena
+            NvlsDataParallel._pending.clear()
+            ParamArena.allocator = NvlsDataParallel._alloc
+
+        def __exit__(self, *exc):
+            from .engine import ParamArena
+            ParamArena.allocator = None
+            return False
+
+    def __init__(self, eng, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib as L
+        self.L, self.eng = L, eng
+        a = eng.arena
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        group = group or dist.group.WORLD
+        if not any(t.data_ptr() == a.flat.data_ptr() for t in NvlsDataParallel._pending):
+            raise RuntimeError("the engine's arenas are not in symmetric memory: build it under NvlsDataParallel.arena_allocation()")
+        self.h_flat = symm_mem.rendezvous(a.flat, group)
+        self.h_grad = symm_mem.rendezvous(a.grad, group)
+        self.partials = symm_mem.empty(64, dtype=torch.float32, device=a.device)
+        self.partials.zero_()
+        self.h_part = symm_mem.rendezvous(self.partials, group)
+        for h in (self.h_flat, self.h_grad, self.h_part):
+            if not h.multicast_ptr:
+                raise RuntimeError("symmetric memory without multicast (NVLS) support on this system")
+        per = a.numel // self.world
+        per -= per % 4
+        self.begin = self.rank * per
+        self.end = a.numel if self.rank == self.world - 1 else (self.rank + 1) * per
+        self.scratch = torch.zeros(4, dtype=torch.float32, device=a.device)        # 16 bytes: double sum + counter
+        # make every rank start from rank 0's parameters
+        dist.broadcast(a.flat, 0, group=group)
+        eng.wplanes.refresh()
+        torch.cuda.synchronize()
+        self.h_flat.barrier(channel=0)
+
+    def step(self, lr: float, max_norm: float = 1.0):
+        """Collective: call on every rank after its backward pass has been queued on the current stream."""
+        L, a = self.L, self.eng.arena
+        self.h_grad.barrier(channel=0)                   # every rank's gradients are complete and visible
+        L.dp_reduce_sumsq(self.h_grad.multicast_ptr, a.grad.data_ptr(), self.begin, self.end, 1.0 / self.world,
+                          self.h_part.multicast_ptr, self.rank, self.scratch.data_ptr(), a.step.data_ptr())
+        self.h_part.barrier(channel=0)                   # all partial norms have landed everywhere
+        L.dp_adam_bcast(self.h_flat.multicast_ptr, a.flat.data_ptr(), a.grad.data_ptr(), a.exp_avg.data_ptr(),
+                        a.exp_avg_sq.data_ptr(), self.begin, self.end, self.partials.data_ptr(), self.world, lr, max_norm,
+                        a.step.data_ptr(), a.grad_norm.data_ptr())
+        self.h_flat.barrier(channel=0)                   # all slices of the new parameters have landed
+        self.eng.wplanes.refresh()

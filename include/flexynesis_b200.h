@@ -220,6 +220,18 @@ int fxn_merge_col_stats(const float* partials, int ntiles, int tile_rows, long l
 int fxn_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                        float beta1, float beta2, float eps, float max_norm, float grad_scale, double* sumsq_scratch,
                        long long* step_counter, float* norm_out, void* stream);
+/* Data-parallel step over NVSwitch multicast (no reference counterpart: pl.Trainer(devices=1), flexynesis/main.py:223).
+ * mc_* are MULTICAST addresses mapping the same-offset arenas of all ranks (torch symmetric memory). Rank `rank` owns the
+ * arena slice [begin, end) (multiples of 4 elements).
+ * fxn_dp_reduce_sumsq: grad_local[slice] = scale * sum over ranks (multimem.ld_reduce), its squared norm is stored into
+ *   slot `rank` of the symmetric partials array on every rank (multimem.st); *step_counter += 1. scratch16: 16 zeroed bytes.
+ * -- callers place a system-wide barrier here --
+ * fxn_dp_adam_bcast: global-norm clip + Adam on the slice, new parameters multicast into every rank's arena. */
+int fxn_dp_reduce_sumsq(const void* mc_grad, float* grad_local, long long begin, long long end, float scale, void* mc_partials,
+                        int rank, void* scratch16, long long* step_counter, void* stream);
+int fxn_dp_adam_bcast(void* mc_param, const float* param_local, const float* grad_local, float* exp_avg, float* exp_avg_sq,
+                      long long begin, long long end, const float* partials, int world, float lr, float beta1, float beta2,
+                      float eps, float max_norm, const long long* step_counter, float* norm_out, void* stream);
 /* Refresh the operand planes of many weight matrices in one launch. segments_dev: device array of nseg records
  * {int64 src_off, rows, cols, ld_src, dst_off, ldp} (element offsets into src / the plane arenas). */
 int fxn_split_planes_multi(const float* src, const void* segments_dev, int nseg, long long max_seg_elems, void* hi,
