@@ -367,6 +367,8 @@ def run_b200(args, w):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its banner there)
         dist.init_process_group("nccl", device_id=dev)
     B = w["B"]
     prob = build_problem(w, rank)                      # this rank's shard of the sample-sharded dataset
