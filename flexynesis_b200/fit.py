@@ -72,6 +72,58 @@ class GraphedStep:
         return self.eng.losses(self.ws)
 
 
+class HostStreamTrainer:
+    """Trains from batches that live in (pinned) HOST memory: every step's inputs are copied host -> device and the
+    step's loss is read back, with the copy of step i+1 overlapped with the compute of step i (two static device buffer
+    sets, one captured graph per set, one copy stream). This is the end-to-end path `bench.py` reports as `e2e`.
+
+    make_batch(buffers) -> batch tuple maps a list of device tensors (same order as `host_tensors`) to the model's
+    batch format."""
+
+    def __init__(self, model, host_tensors, make_batch, lr: Optional[float] = None, allreduce=None, grad_scale: float = 1.0):
+        self.host = [t if t.is_pinned() else t.pin_memory() for t in host_tensors]
+        dev = next(model.parameters()).device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.sets, self.steps, self.ready, self.consumed = [], [], [], []
+        for _ in range(2):
+            bufs = [torch.empty_like(t, device=dev) for t in self.host]
+            for d, s in zip(bufs, self.host):
+                d.copy_(s)
+            self.sets.append(bufs)
+            self.steps.append(GraphedStep(model, make_batch(bufs), lr=lr, resplit_inputs=True, allreduce=allreduce,
+                                          grad_scale=grad_scale))
+            self.ready.append(torch.cuda.Event())
+            self.consumed.append(torch.cuda.Event())
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host)
+        self.launches_per_step = self.steps[0].launches_per_step
+        self._next = 0
+        self._primed = False
+
+    def _start_copy(self, k: int, host_tensors=None):
+        src = self.host if host_tensors is None else host_tensors
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[k])          # the step that last read this buffer set has finished
+            for d, s in zip(self.sets[k], src):
+                d.copy_(s, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+
+    def step(self, next_host_tensors=None) -> float:
+        """One training step on the batch whose copy was started by the previous call; starts the copy of the next batch
+        (`next_host_tensors`, default: the same host batch again) and returns this step's loss (device -> host read)."""
+        k = self._next
+        cur = torch.cuda.current_stream()
+        if not self._primed:
+            self.consumed[0].record(cur); self.consumed[1].record(cur)
+            self._start_copy(k)
+            self._primed = True
+        cur.wait_event(self.ready[k])
+        self.steps[k]()
+        self.consumed[k].record(cur)
+        self._start_copy(1 - k, next_host_tensors)                 # overlaps with the step just queued
+        self._next = 1 - k
+        return float(self.steps[k].losses()["__total__"])          # synchronises with the step, not with the copy
+
+
 def fit(model, dataset, batch_size: int, epochs: int, device="cuda", val_dataset=None, seed: int = 0,
         log_every: int = 0):
     """Train `model` on `dataset` (MultiOmicDataset duck type) with the engine's fused steps. Returns the per-epoch
