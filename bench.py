@@ -269,7 +269,7 @@ def measured_traffic(workload: str):
     or None when no capture of this workload has been taken."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t.get(workload)
+        return t.get(workload, {}).get("traffic")
     except Exception:
         return None
 
