@@ -48,6 +48,7 @@ class BnFwdDesc(C.Structure):
         ("out", C.c_void_p), ("ldo", c_ll),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldp", c_ll),
         ("saved", C.c_void_p),
+        ("stat_rows", c_ll),
     ]
 
 
@@ -62,6 +63,7 @@ class BnBwdDesc(C.Structure):
         ("dV", C.c_void_p), ("ldd", c_ll),
         ("dv_hi", C.c_void_p), ("dv_lo", C.c_void_p), ("ldp", c_ll),
         ("grad_scale", C.c_float), ("accumulate_affine", C.c_int),
+        ("stat_rows", c_ll), ("phase", C.c_int),
     ]
 
 
@@ -234,6 +236,10 @@ def head_out_bwd(D, ldd, rows, sh, W, Cc, logits, ldl, kind, y, acc, coef, weigh
 def cox_fwd(o, ldo, durations, events, n, coef, acc) -> None:
     check(lib.fxn_cox_fwd(C.c_void_p(o), c_ll(ldo), C.c_void_p(durations), C.c_void_p(events), C.c_int(n),
                           C.c_void_p(coef), C.c_void_p(acc), C.c_void_p(stream())), "fxn_cox_fwd")
+
+
+def cox_max_rows() -> int:
+    return int(lib.fxn_cox_max_rows())
 
 
 def total_loss(n, acc, kinds, log_vars, dlog_vars, weighting, out) -> None:

@@ -469,7 +469,7 @@ extern "C" int fxn_bn_act_fwd(const fxn_bn_fwd_desc* d, void* stream_) {
   a.out = d->out; a.ldo = d->ldo;
   a.out_hi = static_cast<__nv_bfloat16*>(d->out_hi); a.out_lo = static_cast<__nv_bfloat16*>(d->out_lo); a.ldp = d->ldp;
   a.saved = d->saved;
-  a.stat_rows = a.rows; a.pcols = a.cols; a.period = 0;
+  a.stat_rows = d->stat_rows > 0 ? d->stat_rows : a.rows; a.pcols = a.cols; a.period = 0;
   {
     // fold narrow contiguous matrices into 64-wide rows (see chan())
     const int f = (a.cols == 8 || a.cols == 16 || a.cols == 32) ? 64 / a.cols : 1;
@@ -503,7 +503,8 @@ extern "C" int fxn_bn_act_bwd(const fxn_bn_bwd_desc* d, void* stream_) {
   a.dv_hi = static_cast<__nv_bfloat16*>(d->dv_hi); a.dv_lo = static_cast<__nv_bfloat16*>(d->dv_lo); a.ldp = d->ldp;
   a.grad_scale = d->grad_scale == 0.f ? 1.f : d->grad_scale;
   a.acc_affine = d->accumulate_affine;
-  a.stat_rows = a.rows; a.pcols = a.cols; a.period = 0;
+  a.stat_rows = d->stat_rows > 0 ? d->stat_rows : a.rows; a.pcols = a.cols; a.period = 0;
+  if (d->phase < 0 || d->phase > 2) return set_error(FXN_ERR_ARG, "fxn_bn_act_bwd: phase must be 0, 1 or 2");
   {
     const int f = (a.cols == 8 || a.cols == 16 || a.cols == 32) ? 64 / a.cols : 1;
     const bool contiguous = a.ldv == a.cols && a.ldg == a.cols && (!a.dV || a.ldd == a.cols) &&
@@ -513,17 +514,21 @@ extern "C" int fxn_bn_act_bwd(const fxn_bn_bwd_desc* d, void* stream_) {
       a.ldv = 64; a.ldg = 64; a.ldd = 64; a.ldp = 64; a.ldm = 64;
     }
   }
-  cudaError_t e = cudaMemsetAsync(a.sums, 0, sizeof(float) * 2 * a.pcols, stream);
-  if (e == cudaSuccess && a.dbias) e = cudaMemsetAsync(a.dbias, 0, sizeof(float) * a.pcols, stream);
-  if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "bn_bwd memset: %s", cudaGetErrorString(e));
   const int width = a.dv_hi ? ((a.cols + 7) & ~7) : a.cols;
   a.rpb = bn_rows_per_block(a.rows, ceil_div(width, BN_COLS));
-  dim3 grid(ceil_div(a.cols, BN_COLS), ceil_div(a.rows, a.rpb));
-  bn_bwd_reduce_kernel<<<grid, BN_THREADS, 0, stream>>>(a);
-  FXN_CHECK_LAUNCH("bn_bwd_reduce");
-  dim3 grid2(ceil_div(width, BN_COLS), ceil_div(a.rows, a.rpb));
-  bn_bwd_apply_kernel<<<grid2, BN_THREADS, 0, stream>>>(a);
-  FXN_CHECK_LAUNCH("bn_bwd_apply");
+  if (d->phase != 2) {
+    cudaError_t e = cudaMemsetAsync(a.sums, 0, sizeof(float) * 2 * a.pcols, stream);
+    if (e == cudaSuccess && a.dbias) e = cudaMemsetAsync(a.dbias, 0, sizeof(float) * a.pcols, stream);
+    if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "bn_bwd memset: %s", cudaGetErrorString(e));
+    dim3 grid(ceil_div(a.cols, BN_COLS), ceil_div(a.rows, a.rpb));
+    bn_bwd_reduce_kernel<<<grid, BN_THREADS, 0, stream>>>(a);
+    FXN_CHECK_LAUNCH("bn_bwd_reduce");
+  }
+  if (d->phase != 1) {
+    dim3 grid2(ceil_div(width, BN_COLS), ceil_div(a.rows, a.rpb));
+    bn_bwd_apply_kernel<<<grid2, BN_THREADS, 0, stream>>>(a);
+    FXN_CHECK_LAUNCH("bn_bwd_apply");
+  }
   return 0;
 }
 

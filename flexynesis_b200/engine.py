@@ -236,7 +236,7 @@ class HeadsBlock:
             mlp = model.MLPs[v]
             c0 = i * self.shp
             mask = None if masks is None else masks.get(f"MLPs.{v}.dropout")
-            L.bn_fwd(V=fptr(ws["Zh"], c0), ldv=ws["Zh"].stride(0), rows=B, cols=self.sh,
+            eng.bn_forward(V=fptr(ws["Zh"], c0), ldv=ws["Zh"].stride(0), rows=B, cols=self.sh,
                      partials=fptr(ws["partials"], c0), ntiles=mt, tile_rows=128, partials_ld=self.width,
                      gamma=a.p(f"MLPs.{v}.batchnorm.weight"), beta=a.p(f"MLPs.{v}.batchnorm.bias"),
                      momentum=MOMENTUM, eps=EPS, train=int(train), act=1, p_drop=0.1 if train else 0.0,
@@ -254,8 +254,33 @@ class HeadsBlock:
                            self.C[v], ws["logits"][v].data_ptr(), self.C[v], kind if kind in (1, 2) else 0, yv,
                            fptr(ws["acc"], 2 * slot))
             if with_loss and kind == 3:
-                L.cox_fwd(ws["logits"][v].data_ptr(), 1, y[self.surv_time].data_ptr(), y[self.surv_event].data_ptr(), B,
-                          ws["coef"].data_ptr(), fptr(ws["acc"], 2 * slot))
+                sync = eng.sync
+                if sync is None:
+                    L.cox_fwd(ws["logits"][v].data_ptr(), 1, y[self.surv_time].data_ptr(), y[self.surv_event].data_ptr(),
+                              B, ws["coef"].data_ptr(), fptr(ws["acc"], 2 * slot))
+                else:
+                    # global risk sets: gather (o, t, e) of every rank, evaluate the partial likelihood on world * B rows,
+                    # keep this rank's coefficients (x world: the gradient all-reduce averages over ranks)
+                    n = sync.world * B
+                    if n > L.cox_max_rows():
+                        raise L.FxnError(f"global Cox batch of {n} rows exceeds the kernel limit {L.cox_max_rows()}")
+                    og = sync.all_gather(ws["logits"][v].reshape(-1)).view(-1)
+                    tg = sync.all_gather(y[self.surv_time].reshape(-1)).view(-1)
+                    eg = sync.all_gather(y[self.surv_event].reshape(-1)).view(-1)
+                    cg = torch.empty(n, device=eng.device)
+                    L.cox_fwd(og.data_ptr(), 1, tg.data_ptr(), eg.data_ptr(), n, cg.data_ptr(), fptr(ws["acc"], 2 * slot))
+                    torch.mul(cg[sync.rank * B:(sync.rank + 1) * B], float(sync.world), out=ws["coef"])
+        if with_loss and eng.sync is not None:
+            # means over the valid labels of the GLOBAL batch: count_global / world replaces the local count
+            sync = eng.sync
+            slots = [self.loss_names.index(v) for v in self.vars if self.kinds[v] in (1, 2)]
+            if slots:
+                if getattr(self, "_sync_slots", None) is None:
+                    self._sync_slots = torch.tensor(slots, device=eng.device)
+                idx = self._sync_slots
+                cnt = ws["acc"][idx, 1].contiguous()
+                sync.all_reduce(cnt)
+                ws["acc"][idx, 1] = cnt / float(sync.world)
 
     def total(self, ws):
         L.total_loss(self.n_losses, ws["acc"].data_ptr(), self.kinds_dev.data_ptr(),
@@ -285,13 +310,13 @@ class HeadsBlock:
                            a.g(f"MLPs.{v}.layer_out.bias") if has_b else None)
             mask = None if masks is None else masks.get(f"MLPs.{v}.dropout")
             dz = ws["dZh"].cols_view(c0, self.sh)
-            L.bn_bwd(V=fptr(ws["Zh"], c0), ldv=ws["Zh"].stride(0), dOut=fptr(ws["dDh"], c0), ldg=ws["dDh"].stride(0),
-                     rows=B, cols=self.sh, gamma=a.p(f"MLPs.{v}.batchnorm.weight"), beta=a.p(f"MLPs.{v}.batchnorm.bias"),
-                     saved=ws["saved"][i].data_ptr(), act=1, p_drop=0.1,
-                     mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
-                     seed=eng.seed + 7919 * (i + 1), seed_dev=eng.arena.step.data_ptr(), pre_act=0,
-                     sums=ws["sums"][i].data_ptr(), dgamma=a.g(f"MLPs.{v}.batchnorm.weight"),
-                     dbeta=a.g(f"MLPs.{v}.batchnorm.bias"), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+            eng.bn_backward(V=fptr(ws["Zh"], c0), ldv=ws["Zh"].stride(0), dOut=fptr(ws["dDh"], c0),
+                            ldg=ws["dDh"].stride(0), rows=B, cols=self.sh, gamma=a.p(f"MLPs.{v}.batchnorm.weight"),
+                            beta=a.p(f"MLPs.{v}.batchnorm.bias"), saved=ws["saved"][i].data_ptr(), act=1, p_drop=0.1,
+                            mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
+                            seed=eng.seed + 7919 * (i + 1), seed_dev=eng.arena.step.data_ptr(), pre_act=0,
+                            sums=ws["sums"][i], dgamma=a.view(f"MLPs.{v}.batchnorm.weight", a.grad),
+                            dbeta=a.view(f"MLPs.{v}.batchnorm.bias", a.grad), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
             # dW1_v [sh x L] = dZh_v^T * F
             L.gemm(self.sh, self.L, B, dz, 1, Fp, 1, C_ptr=a.g(f"MLPs.{v}.layer_1.weight"), ldc=self.L, splitk=-1)
         # dF [B x L] = dZh_cat * W1cat   (+ column sums -> bias gradient of whatever produced F)
@@ -320,6 +345,7 @@ class EngineBase:
         self.ws: Dict[int, dict] = {}
         self.side: List[torch.cuda.Stream] = []
         self.parallel_encoders = True
+        self.sync = None          # parallel.GlobalBatchSync: N ranks reproduce one step on the concatenated batch
 
     def _finish_init(self, n_side: int):
         """Call at the end of a subclass constructor, after every weight plane has been registered."""
@@ -351,6 +377,42 @@ class EngineBase:
                 ev = torch.cuda.Event()
                 ev.record(st)
                 main.wait_event(ev)
+
+    # -- BatchNorm blocks (optionally with global-batch statistics, parallel.GlobalBatchSync) --
+    def bn_forward(self, **kw):
+        """fxn_bn_act_fwd; with `self.sync` in train mode the local tile partials are merged into one (sum, M2) record,
+        all-gathered, and the norm runs on the statistics of world * rows rows."""
+        s = self.sync
+        if s is None or not kw.get("train"):
+            L.bn_fwd(**kw)
+            return
+        rows, cols = int(kw["rows"]), int(kw["cols"])
+        rec = torch.empty(2, cols, device=self.device)
+        L.merge_col_stats(kw["partials"], kw["ntiles"], kw["tile_rows"], rows, cols, kw.get("partials_ld") or cols,
+                          rec.data_ptr())
+        allrec = s.all_gather(rec)                              # [world, 2, cols]
+        kw.update(partials=allrec.data_ptr(), ntiles=s.world, tile_rows=rows, partials_ld=cols, stat_rows=s.world * rows)
+        L.bn_fwd(**kw)
+
+    def bn_backward(self, *, sums: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor, accumulate_affine: int = 0, **kw):
+        """fxn_bn_act_bwd; `sums` is the [2 * cols] scratch tensor, dgamma / dbeta are views of the gradient arena. With
+        `self.sync`: column reductions over the local rows (phase 1; they ARE this rank's share of dgamma / dbeta), sum
+        all-reduce, apply pass with the global sums and the global row count (phase 2)."""
+        s = self.sync
+        if s is None:
+            L.bn_bwd(sums=sums.data_ptr(), dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(),
+                     accumulate_affine=accumulate_affine, **kw)
+            return
+        cols = int(kw["cols"])
+        flat = sums.view(-1)
+        L.bn_bwd(sums=flat.data_ptr(), phase=1, **kw)
+        if accumulate_affine:
+            dbeta.view(-1).add_(flat[:cols]); dgamma.view(-1).add_(flat[cols:2 * cols])
+        else:
+            dbeta.view(-1).copy_(flat[:cols]); dgamma.view(-1).copy_(flat[cols:2 * cols])
+        red = flat[:2 * cols]
+        s.all_reduce(red)
+        L.bn_bwd(sums=flat.data_ptr(), phase=2, stat_rows=s.world * int(kw["rows"]), **kw)
 
     def ensure_fresh(self):
         """Weight planes follow the fp32 parameters: refresh them if anything outside optimizer_step (a torch optimizer,
@@ -481,7 +543,7 @@ class TrunkEngine(EngineBase):
                       L.col_stats(fptr(ws["Z"][i], r0 * hp), hp, B, h, 128, ws["partials"][i][g].data_ptr())
                   mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
                   D = ws["D"][i].rows_view(r0, B)
-                  L.bn_fwd(V=fptr(ws["Z"][i], r0 * hp), ldv=hp, rows=B, cols=h,
+                  self.bn_forward(V=fptr(ws["Z"][i], r0 * hp), ldv=hp, rows=B, cols=h,
                            partials=ws["partials"][i][g].data_ptr(), ntiles=L.stat_tiles(B), tile_rows=128,
                            gamma=a.p(f"encoders.{i}.batchnorm.weight"), beta=a.p(f"encoders.{i}.batchnorm.bias"),
                            momentum=MOMENTUM, eps=EPS, train=int(train), act=1, p_drop=0.1 if train else 0.0,
@@ -527,15 +589,17 @@ class TrunkEngine(EngineBase):
                   mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
                   dz = ws["dZ"][i].rows_view(r0, B)
                   first = g == 0
-                  L.bn_bwd(V=fptr(ws["Z"][i], r0 * hp), ldv=hp, dOut=fptr(ws["dD"][i], r0 * hp), ldg=hp, rows=B, cols=h,
-                           gamma=a.p(f"encoders.{i}.batchnorm.weight"), beta=a.p(f"encoders.{i}.batchnorm.bias"),
-                           saved=ws["saved"][i][g].data_ptr(), act=1, p_drop=0.1,
-                           mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
-                           seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=a.step.data_ptr(), pre_act=0,
-                           sums=ws["sums"][i][g].data_ptr(),
-                           dgamma=a.g(f"encoders.{i}.batchnorm.weight"), dbeta=a.g(f"encoders.{i}.batchnorm.bias"),
-                           accumulate_affine=0 if first else 1,   # affine grads add up over the three triplet passes
-                           dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+                  self.bn_backward(V=fptr(ws["Z"][i], r0 * hp), ldv=hp, dOut=fptr(ws["dD"][i], r0 * hp), ldg=hp, rows=B,
+                                   cols=h, gamma=a.p(f"encoders.{i}.batchnorm.weight"),
+                                   beta=a.p(f"encoders.{i}.batchnorm.bias"), saved=ws["saved"][i][g].data_ptr(), act=1,
+                                   p_drop=0.1, mask=None if mask is None else mask.data_ptr(),
+                                   ldm=0 if mask is None else mask.stride(0),
+                                   seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=a.step.data_ptr(),
+                                   pre_act=0, sums=ws["sums"][i][g],
+                                   dgamma=a.view(f"encoders.{i}.batchnorm.weight", a.grad),
+                                   dbeta=a.view(f"encoders.{i}.batchnorm.bias", a.grad),
+                                   accumulate_affine=0 if first else 1,   # affine grads add up over the three triplet passes
+                                   dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
               # dW1_i = dZ_i^T * X_i
               L.gemm(h, self.d[i], R, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_1.weight"),
                      ldc=self.d[i], splitk=-1)
@@ -705,7 +769,7 @@ class VAEEngine(EngineBase):
         bn = self.model.get_submodule(prefix).hidden_layers[2]
         L.gemm(B, h, K, inp, 0, wplanes, 0, C_ptr=A.data_ptr(), ldc=hp, bias=a.p(f"{prefix}.hidden_layers.0.bias"),
                epi_act=6, colstats=ws["partials" + tag][i].data_ptr() if train else None, stats_mode=2)
-        L.bn_fwd(V=A.data_ptr(), ldv=hp, rows=B, cols=h, partials=ws["partials" + tag][i].data_ptr(),
+        self.bn_forward(V=A.data_ptr(), ldv=hp, rows=B, cols=h, partials=ws["partials" + tag][i].data_ptr(),
                  ntiles=L.stat_tiles(B), tile_rows=128, gamma=a.p(f"{prefix}.hidden_layers.2.weight"),
                  beta=a.p(f"{prefix}.hidden_layers.2.bias"), momentum=MOMENTUM, eps=EPS, train=int(train), act=0,
                  p_drop=0.0, out_hi=Y.hi_ptr, out_lo=Y.lo_ptr, ldp=Y.ld, saved=ws["saved" + tag][i].data_ptr(),
@@ -716,12 +780,12 @@ class VAEEngine(EngineBase):
         a = self.arena
         B, h, hp = ws["B"], self.h[i], pad8(self.h[i])
         dz = ws["dZ" + tag][i]
-        L.bn_bwd(V=ws["A" + tag][i].data_ptr(), ldv=hp, dOut=ws["dY" + tag][i].data_ptr(), ldg=hp, rows=B, cols=h,
-                 gamma=a.p(f"{prefix}.hidden_layers.2.weight"), beta=a.p(f"{prefix}.hidden_layers.2.bias"),
-                 saved=ws["saved" + tag][i].data_ptr(), act=0, p_drop=0.0, pre_act=1,
-                 sums=ws["sums" + tag][i].data_ptr(), dgamma=a.g(f"{prefix}.hidden_layers.2.weight"),
-                 dbeta=a.g(f"{prefix}.hidden_layers.2.bias"), dbias=a.g(f"{prefix}.hidden_layers.0.bias"),
-                 dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+        self.bn_backward(V=ws["A" + tag][i].data_ptr(), ldv=hp, dOut=ws["dY" + tag][i].data_ptr(), ldg=hp, rows=B, cols=h,
+                         gamma=a.p(f"{prefix}.hidden_layers.2.weight"), beta=a.p(f"{prefix}.hidden_layers.2.bias"),
+                         saved=ws["saved" + tag][i].data_ptr(), act=0, p_drop=0.0, pre_act=1,
+                         sums=ws["sums" + tag][i], dgamma=a.view(f"{prefix}.hidden_layers.2.weight", a.grad),
+                         dbeta=a.view(f"{prefix}.hidden_layers.2.bias", a.grad),
+                         dbias=a.g(f"{prefix}.hidden_layers.0.bias"), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
 
     # ---- forward: encoders -> latent -> decoders | heads | MMD ----
     def _forward(self, ws, y, train: bool, noise, with_loss: bool, want_xhat: bool = False):
@@ -973,7 +1037,7 @@ class GNNEngine(EngineBase):
             else:
                 dst = ws["Dlast"] if last else ws["D"][k]
                 kw = dict(out=dst.data_ptr(), ldo=emb)
-            L.bn_fwd(V=ws["O"][k].data_ptr(), ldv=emb, rows=rows, cols=emb, partials=ws["merged"][k].data_ptr(), ntiles=1,
+            self.bn_forward(V=ws["O"][k].data_ptr(), ldv=emb, rows=rows, cols=emb, partials=ws["merged"][k].data_ptr(), ntiles=1,
                      tile_rows=rows, gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
                      momentum=MOMENTUM, eps=EPS, train=int(train), act=self.act, p_drop=self.p_drop if train else 0.0,
                      mask=None if mask is None else mask.data_ptr(), ldm=emb, seed=self.seed + 7 + 131 * k,
@@ -1012,13 +1076,13 @@ class GNNEngine(EngineBase):
         for k in reversed(range(K)):
             fin = self.F if k == 0 else emb
             mask = None if masks is None else masks.get(f"encoders.0.dropout.{k}")
-            L.bn_bwd(V=ws["O"][k].data_ptr(), ldv=emb, dOut=ws["dD"].data_ptr(), ldg=emb, rows=rows, cols=emb,
-                     gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
-                     saved=ws["saved"][k].data_ptr(), act=self.act, p_drop=self.p_drop,
-                     mask=None if mask is None else mask.data_ptr(), ldm=emb, seed=self.seed + 7 + 131 * k,
-                     seed_dev=a.step.data_ptr(), pre_act=0, sums=ws["sums"][k].data_ptr(),
-                     dgamma=a.g(f"encoders.0.bns.{k}.weight"), dbeta=a.g(f"encoders.0.bns.{k}.bias"),
-                     dV=ws["dO"].data_ptr(), ldd=emb)
+            self.bn_backward(V=ws["O"][k].data_ptr(), ldv=emb, dOut=ws["dD"].data_ptr(), ldg=emb, rows=rows, cols=emb,
+                             gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
+                             saved=ws["saved"][k].data_ptr(), act=self.act, p_drop=self.p_drop,
+                             mask=None if mask is None else mask.data_ptr(), ldm=emb, seed=self.seed + 7 + 131 * k,
+                             seed_dev=a.step.data_ptr(), pre_act=0, sums=ws["sums"][k],
+                             dgamma=a.view(f"encoders.0.bns.{k}.weight", a.grad),
+                             dbeta=a.view(f"encoders.0.bns.{k}.bias", a.grad), dV=ws["dO"].data_ptr(), ldd=emb)
             L.gcn_bwd(xin[k].data_ptr(), ws["dO"].data_ptr(), B, N, fin, emb, self.csr_in, self.csr_out,
                       a.p(f"encoders.0.convs.{k}.lin.weight"), a.g(f"encoders.0.convs.{k}.lin.weight"),
                       a.g(f"encoders.0.convs.{k}.bias"), ws["dD"].data_ptr() if k > 0 else None)

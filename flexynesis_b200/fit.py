@@ -27,6 +27,9 @@ class GraphedStep:
         groups, _ = model._split_batch(batch)
         eng = model.engine(groups[0][0].device)
         self.eng = eng
+        if eng.sync is not None:
+            raise NotImplementedError("global-batch sync (parallel.GlobalBatchSync) issues host-driven collectives between "
+                                      "kernels and runs eagerly: use model.fit_step, not a captured graph")
         lr = float(model.config["lr"] if lr is None else lr)
         eng.inputs.enabled = not resplit_inputs
         s = torch.cuda.Stream()

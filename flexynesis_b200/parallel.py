@@ -155,3 +155,56 @@ class NvlsDataParallel:
                         a.step.data_ptr(), a.grad_norm.data_ptr())
         self.h_flat.barrier(channel=0)                   # all slices of the new parameters have landed
         self.eng.wplanes.refresh()
+
+
+class GlobalBatchSync:
+    """Collectives that make an N-rank step equal to ONE step on the concatenated batch (SURVEY.md section 8e, items 1, 2
+    and 6) instead of PyTorch-DDP's per-rank semantics:
+
+      * BatchNorm: every rank Chan-merges its row-tile partials into one (sum, M2) record, the records are all-gathered
+        and the norm kernel merges them (`stat_rows` = global rows); backward sum-all-reduces (sum g, sum g*xhat)
+        between the reduction and the apply pass (fxn_bn_act_bwd phases 1 / 2).
+      * MSE / cross-entropy means run over the valid labels of the GLOBAL batch: the valid counts are all-reduced and
+        each rank normalises by count_global / world, so the mean over ranks of the rank losses (and of their
+        gradients, which is what the gradient all-reduce forms) is the global mean.
+      * Cox: risk scores, durations and events are all-gathered and the partial likelihood is evaluated over the global
+        risk sets; each rank back-propagates the coefficients of its own rows.
+
+    Every rank must hold the same number of rows per step. The supervised_vae MMD term couples all pairs of the batch
+    and stays per-rank (documented in DESIGN.md). Works over any torch.distributed backend (NCCL on GPUs; gloo in the
+    tests, also for CUDA tensors)."""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("GlobalBatchSync needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.calls = 0
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        """[...] on every rank -> [world, ...] (rank-major), same on every rank."""
+        self.calls += 1
+        t = t.contiguous()
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        return torch.stack(out, 0)
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum over ranks (t must be contiguous)."""
+        self.calls += 1
+        dist.all_reduce(t, group=self.group)
+        return t
+
+
+def merge_stat_records(records: torch.Tensor, rows_per_rank: int):
+    """Host restatement of what fxn_bn_act_fwd does with gathered records (used by the CPU protocol test):
+    records [world, 2, cols] = per-rank (sum, M2 about the rank mean) over rows_per_rank rows -> (mean, biased var) of the
+    world * rows_per_rank rows, by Chan's parallel formula."""
+    world = records.shape[0]
+    n = float(rows_per_rank)
+    total = records[:, 0].sum(0)
+    mean = total / (world * n)
+    d = records[:, 0] / n - mean
+    m2 = (records[:, 1] + n * d * d).sum(0)
+    return mean, m2 / (world * n)

@@ -114,6 +114,9 @@ typedef struct fxn_bn_fwd_desc {
   float* out; long long ldo;                 /* optional fp32 output */
   void* out_hi; void* out_lo; long long ldp; /* optional planes of the output */
   float* saved;
+  long long stat_rows;                       /* rows the batch statistics cover (0 = rows). Larger than `rows` when the
+                                                partials were gathered from several ranks (global-batch BatchNorm): the
+                                                tiles then describe stat_rows rows, this call normalises its own `rows` */
 } fxn_bn_fwd_desc;
 int fxn_bn_act_fwd(const fxn_bn_fwd_desc* d, void* stream);
 
@@ -132,6 +135,10 @@ typedef struct fxn_bn_bwd_desc {
   void* dv_hi; void* dv_lo; long long ldp;
   float grad_scale;      /* multiplies dOut; 0 means 1 */
   int accumulate_affine; /* dgamma/dbeta += instead of = (a module applied several times per step) */
+  long long stat_rows;   /* rows the forward statistics covered (0 = rows); see fxn_bn_fwd_desc */
+  int phase;             /* 0: whole backward. 1: only the column reductions into `sums` (sum g, sum g*xhat over this
+                            call's rows). 2: only the apply pass, reading `sums` as given -- a data-parallel caller
+                            sum-all-reduces `sums` between phase 1 and phase 2 (SyncBN backward) */
 } fxn_bn_bwd_desc;
 int fxn_bn_act_bwd(const fxn_bn_bwd_desc* d, void* stream);
 
