@@ -129,8 +129,12 @@ def _bn_ptrs(bn: nn.BatchNorm1d):
 
 
 class InputCache:
-    """Operand planes of input matrices, keyed by (storage pointer, shape, version): a resident dataset that is fed
-    unchanged step after step (full-batch training) is split once."""
+    """Operand planes of input matrices, keyed by (address, shape, strides, version counter, writer tag): a resident
+    dataset that is fed unchanged step after step (full-batch training) is split once. Each entry HOLDS the tensor it
+    was made from: while the entry lives that storage cannot be freed and handed to another batch by the caching
+    allocator, so an equal key really means "same memory, not written through torch since" (a loop that builds a fresh
+    batch tensor every step misses and re-splits, as it must). Writers that bypass torch (fxn_gather_rows through a raw
+    pointer) bump `_fxn_tag` on the tensor."""
 
     def __init__(self):
         self.entries = {}
@@ -140,11 +144,12 @@ class InputCache:
         if not self.enabled:
             L.split_planes(x, dst)
             return
-        key = (x.data_ptr(), tuple(x.shape), x._version, getattr(x, "_fxn_tag", None))
-        if self.entries.get(slot) == key:
+        key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x._version, getattr(x, "_fxn_tag", None))
+        hit = self.entries.get(slot)
+        if hit is not None and hit[0] == key:
             return
         L.split_planes(x, dst)
-        self.entries[slot] = key
+        self.entries[slot] = (key, x)
 
     def invalidate(self):
         self.entries.clear()

@@ -24,17 +24,85 @@ FULL = {
 }
 
 
+def _center_gap(v: torch.Tensor) -> torch.Tensor:
+    """v [B, units]: values whose SIGN is an activation gate. Returns a per-unit shift that puts zero in the middle of the
+    widest gap between consecutive sorted values near the zero crossing."""
+    s, _ = torch.sort(v.detach(), 0)
+    B = s.shape[0]
+    idx = (s < 0).sum(0)                                        # first non-negative position per unit
+    pos = (idx[None, :] + torch.arange(-8, 9)[:, None]).clamp(0, B - 1)
+    win = torch.gather(s, 0, pos)                               # 17 consecutive sorted values around the crossing
+    gaps = win[1:] - win[:-1]
+    j = gaps.argmax(0)
+    lo = torch.gather(win, 0, j[None, :])[0]
+    hi = torch.gather(win, 0, (j + 1)[None, :])[0]
+    delta = -(lo + hi) / 2
+    assert float((v + delta).abs().min()) > 1e-5, "could not establish a gate margin"
+    return delta
+
+
+def _bn_train(P, prefix, z):
+    return (z - z.mean(0)) * torch.rsqrt(z.var(0, unbiased=False) + 1e-5) * P[prefix + ".weight"] + P[prefix + ".bias"]
+
+
+def gate_safe_state(spec, P, batch):
+    """ReLU / LeakyReLU gates are discontinuities of the gradient. At these sizes (millions of gated values per layer)
+    a seeded init always has pre-activations within fp32 rounding (1e-6) of zero, where two correct implementations
+    may gate differently and one sample's term of every upstream gradient flips with it (1/sqrt(B) of an entry, far
+    above 1e-3). This nudges the bias that sits right in front of each gate (< 1e-2, per unit, in forward order) so that
+    every gated value keeps a margin of >= 1e-5 from zero; the comparison that follows is then strict everywhere.
+    Returns the noise tensors (dropout masks, epsilon, MMD priors) drawn once and replayed on both sides."""
+    import copy
+    import torch.nn.functional as Fn
+    from oracle.restatement import Noise, forward, vae_encoder, _fused_embedding
+    torch.manual_seed(1000)
+    n0 = Noise()
+    with torch.no_grad():
+        forward(copy.deepcopy(P), spec, batch, True, n0)
+        given = dict(n0.record)
+        xs = list(batch[0].values())
+        if spec.model == "DirectPred":
+            for i, x in enumerate(xs):
+                z = Fn.linear(x, P[f"encoders.{i}.layer_1.weight"], P[f"encoders.{i}.layer_1.bias"])
+                P[f"encoders.{i}.batchnorm.bias"] += _center_gap(_bn_train(P, f"encoders.{i}.batchnorm", z))
+            emb = _fused_embedding(copy.deepcopy(P), spec, xs, True, Noise(given))
+        else:
+            for i, x in enumerate(xs):
+                z = Fn.linear(x, P[f"encoders.{i}.hidden_layers.0.weight"], P[f"encoders.{i}.hidden_layers.0.bias"])
+                P[f"encoders.{i}.hidden_layers.0.bias"] += _center_gap(z)
+            Pc = copy.deepcopy(P)
+            means, logvars = zip(*[vae_encoder(Pc, f"encoders.{i}", x, True) for i, x in enumerate(xs)])
+            mean = Fn.linear(torch.cat(means, 1), P["FC_mean.weight"], P["FC_mean.bias"])
+            log_var = Fn.linear(torch.cat(logvars, 1), P["FC_log_var.weight"], P["FC_log_var.bias"])
+            emb = mean + log_var * given["epsilon"]
+            for i in range(len(xs)):
+                z = Fn.linear(emb, P[f"decoders.{i}.hidden_layers.0.weight"], P[f"decoders.{i}.hidden_layers.0.bias"])
+                P[f"decoders.{i}.hidden_layers.0.bias"] += _center_gap(z)
+        for v in spec.variables:
+            z = Fn.linear(emb, P[f"MLPs.{v}.layer_1.weight"], P[f"MLPs.{v}.layer_1.bias"])
+            P[f"MLPs.{v}.batchnorm.bias"] += _center_gap(_bn_train(P, f"MLPs.{v}.batchnorm", z))
+    return given
+
+
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("name", list(FULL))
 def test_full_size_step_matches_oracle(name):
+    from oracle.restatement import init_params, synthetic_batch
     spec, B = FULL[name]
-    P0, batch, steps, _ = oracle_reference(spec, B, 1e-3, steps=1)
+    torch.manual_seed(0)
+    P = init_params(spec)
+    dat, y = synthetic_batch(spec, B, 0)
+    batch = (dat, y, None)
+    given = gate_safe_state(spec, P, batch)
+    P0, batch, steps, _ = oracle_reference(spec, B, 1e-3, steps=1, batch=batch, P=P, given=given)
+    st = steps[0]
+    st["flagged"] = {}                    # every gate has a verified margin: strict comparison of all gradients
     model = build_model(spec, batch, 1e-3, P0)
     model.train()
     cb = to_cuda(batch)
     rep = Report()
-    sync_state(model, steps[0]["P_before"])
-    compare_step(rep, model, spec, batch, cb, steps[0], 0, steps[0]["P_before"], 1e-3)
+    sync_state(model, st["P_before"])
+    compare_step(rep, model, spec, batch, cb, st, 0, st["P_before"], 1e-3)
     rep.finish()
 
 

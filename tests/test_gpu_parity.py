@@ -236,11 +236,13 @@ def test_engine_matches_reference_golden(path):
     rep.finish()
 
 
-def oracle_reference(spec, B, lr, steps, seed=0, batch=None, edge_index=None):
-    """Run the CPU oracle for `steps` steps; records pre-step state, noise, results and Adam moments."""
+def oracle_reference(spec, B, lr, steps, seed=0, batch=None, edge_index=None, P=None, given=None):
+    """Run the CPU oracle for `steps` steps; records pre-step state, noise, results and Adam moments. `P` (optional):
+    start from these parameters instead of a seeded init; `given` (optional): noise tensors replayed in every step."""
     torch.manual_seed(seed)
     from oracle.restatement import init_params
-    P = init_params(spec)
+    if P is None:
+        P = init_params(spec)
     P0 = {k: v.clone() for k, v in P.items()}
     if batch is None:
         dat, y = synthetic_batch(spec, B, seed)
@@ -252,7 +254,7 @@ def oracle_reference(spec, B, lr, steps, seed=0, batch=None, edge_index=None):
     out = []
     for s in range(steps):
         torch.manual_seed(1000 + s)
-        noise = Noise()
+        noise = Noise(given)
         P_before = {k: v.detach().clone() for k, v in P.items()}
         adam_before = {k: {kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in tr.opt.state[P[k]].items()}
                        for k in tr.names if P[k] in tr.opt.state}
