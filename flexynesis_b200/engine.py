@@ -322,12 +322,17 @@ class HeadsBlock:
                             seed=eng.seed + 7919 * (i + 1), seed_dev=eng.arena.step.data_ptr(), pre_act=0,
                             sums=ws["sums"][i], dgamma=a.view(f"MLPs.{v}.batchnorm.weight", a.grad),
                             dbeta=a.view(f"MLPs.{v}.batchnorm.bias", a.grad), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
-            # dW1_v [sh x L] = dZh_v^T * F
-            L.gemm(self.sh, self.L, B, dz, 1, Fp, 1, C_ptr=a.g(f"MLPs.{v}.layer_1.weight"), ldc=self.L, splitk=-1)
-        # dF [B x L] = dZh_cat * W1cat   (+ column sums -> bias gradient of whatever produced F)
+        # dF [B x L] = dZh_cat * W1cat   (+ column sums -> bias gradient of whatever produced F): the critical path
+        ev = eng._mark()
         L.gemm(B, self.L, self.width, ws["dZh"], 0, self.w1_planes(), 1,
                C_ptr=None if dF_f32 is None else dF_f32.data_ptr(), ldc=0 if dF_f32 is None else dF_f32.stride(0),
                out=dF, colstats=dbias_ptr, stats_mode=3 if dbias_ptr is not None else 0, accumulate=accumulate)
+
+        def wgrads():
+            for i, v in enumerate(self.vars):      # dW1_v [sh x L] = dZh_v^T * F
+                dz = ws["dZh"].cols_view(i * self.shp, self.sh)
+                L.gemm(self.sh, self.L, B, dz, 1, Fp, 1, C_ptr=a.g(f"MLPs.{v}.layer_1.weight"), ldc=self.L, splitk=-1)
+        eng._aux_run(len(eng.aux) - 1, wgrads, after=ev)       # joined by the engine at the end of its backward pass
         return True
 
 
@@ -361,6 +366,10 @@ class EngineBase:
         # independent per-modality chains run on parallel streams (they become parallel branches of the captured
         # CUDA graph) so that small tiles of one modality fill the SMs the other leaves idle
         self.side = [torch.cuda.Stream(device=self.device) for _ in range(max(n_side, 0))]
+        # one more stream per modality chain (+1 for the heads) for work that is OFF the critical path of the backward
+        # pass: the weight gradients of the small layers run beside the dgrad -> BatchNorm -> dgrad chain they hang off
+        self.aux = [torch.cuda.Stream(device=self.device) for _ in range(max(n_side, 0) + 2)]
+        self._aux_used = set()
 
     # -- helpers --
     def _stream_for(self, i: int):
@@ -374,6 +383,34 @@ class EngineBase:
             ev.record(torch.cuda.current_stream())
             for st in self.side:
                 st.wait_event(ev)
+
+    def _mark(self):
+        """Event recorded on the current stream (a dependency point for _aux_run)."""
+        if not self.parallel_encoders:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def _aux_run(self, k: int, fn, after=None):
+        """Run fn() on auxiliary stream k, ordered after `after` (an event from _mark(); default: everything queued so far
+        on the current stream). It becomes a parallel branch of a captured graph; _aux_join(k) orders the current stream
+        after it. Launch the critical-path kernel BEFORE calling this so that its CTAs are dispatched first."""
+        if not self.parallel_encoders:
+            fn()
+            return
+        aux = self.aux[k]
+        aux.wait_event(after if after is not None else self._mark())
+        with torch.cuda.stream(aux):
+            fn()
+        self._aux_used.add(k)
+
+    def _aux_join(self, k: int):
+        if k in self._aux_used:
+            ev = torch.cuda.Event()
+            ev.record(self.aux[k])
+            torch.cuda.current_stream().wait_event(ev)
+            self._aux_used.discard(k)
 
     def _join(self):
         if self.parallel_encoders and self.side:
@@ -580,15 +617,19 @@ class TrunkEngine(EngineBase):
               E_p = ws["Ecat_p"].cols_view(i * Lp, Lt)
               has_b2 = enc.layer_out.bias is not None
               if self.fused:
+                  ev = self._mark()
                   # dE_i = dF * Wf[:, iL:(i+1)L]   (+ column sums -> d layer_out.bias)
                   L.gemm(R, Lt, Lt, ws["dF_p"], 0, self.wf_planes(i), 1, out=dE,
                          colstats=a.g(f"encoders.{i}.layer_out.bias") if has_b2 else None, stats_mode=3)
-                  # dWf[:, iL:(i+1)L] = dF^T * E_i
-                  L.gemm(Lt, Lt, R, ws["dF_p"], 1, E_p, 1, C_ptr=fptr(a.grad, a.offset["fusion_block.weight"] + i * Lt),
-                         ldc=self.n * Lt, splitk=-1)
-              # dD_i = dE_i * W2_i ; dW2_i = dE_i^T * D_i
+                  # dWf[:, iL:(i+1)L] = dF^T * E_i        (beside it: needs dF only)
+                  self._aux_run(i, lambda i=i, E_p=E_p: L.gemm(
+                      Lt, Lt, R, ws["dF_p"], 1, E_p, 1, C_ptr=fptr(a.grad, a.offset["fusion_block.weight"] + i * Lt),
+                      ldc=self.n * Lt, splitk=-1), after=ev)
+              # dD_i = dE_i * W2_i (critical path) ; dW2_i = dE_i^T * D_i (beside it)
+              ev = self._mark()
               L.gemm(R, h, Lt, dE, 0, self.wp(self.w2[i]), 1, C_ptr=ws["dD"][i].data_ptr(), ldc=hp)
-              L.gemm(Lt, h, R, dE, 1, ws["D"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_out.weight"), ldc=h, splitk=-1)
+              self._aux_run(i, lambda i=i, dE=dE, h=h: L.gemm(
+                  Lt, h, R, dE, 1, ws["D"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_out.weight"), ldc=h, splitk=-1), after=ev)
               for g in range(G):
                   r0 = g * Bp
                   mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
@@ -608,7 +649,9 @@ class TrunkEngine(EngineBase):
               # dW1_i = dZ_i^T * X_i
               L.gemm(h, self.d[i], R, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_1.weight"),
                      ldc=self.d[i], splitk=-1)
+              self._aux_join(i)
         self._join()
+        self._aux_join(len(self.aux) - 1)          # the heads' weight gradients
 
     # -- full steps --
     def forward_backward(self, x_groups, y, masks=None):
@@ -931,6 +974,7 @@ class VAEEngine(EngineBase):
                 L.gemm(h, d, B, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.hidden_layers.0.weight"),
                        ldc=d, splitk=-1)
         self._join()
+        self._aux_join(len(self.aux) - 1)          # the heads' weight gradients
         return ws
 
     def evaluate(self, x_groups, y=None, train_mode: bool = False, masks=None, want_xhat: bool = False):
@@ -1091,6 +1135,7 @@ class GNNEngine(EngineBase):
             L.gcn_bwd(xin[k].data_ptr(), ws["dO"].data_ptr(), B, N, fin, emb, self.csr_in, self.csr_out,
                       a.p(f"encoders.0.convs.{k}.lin.weight"), a.g(f"encoders.0.convs.{k}.lin.weight"),
                       a.g(f"encoders.0.convs.{k}.bias"), ws["dD"].data_ptr() if k > 0 else None)
+        self._aux_join(len(self.aux) - 1)          # the heads' weight gradients
         return ws
 
     def evaluate(self, x_groups, y=None, train_mode: bool = False, masks=None):

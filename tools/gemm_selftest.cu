@@ -175,7 +175,10 @@ __global__ void fill_bf16_kernel(__nv_bfloat16* p, long long n, unsigned seed, f
 static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn, int nterms, int block_n, int splitk) {
   const long long a_rows = a_mn ? K : M, a_cols = a_mn ? M : K;
   const long long b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
-  const long long lda = r8(a_cols), ldb = r8(b_cols);
+  // FXN_TEST_LDALIGN (elements): leading-dimension alignment of the operand planes (8 = the minimum TMA accepts; 64 makes
+  // every 128-byte box row start on a cache line)
+  const long long al = getenv("FXN_TEST_LDALIGN") ? atoll(getenv("FXN_TEST_LDALIGN")) : 8;
+  const long long lda = (a_cols + al - 1) / al * al, ldb = (b_cols + al - 1) / al * al;
   __nv_bfloat16 *Ah, *Al, *Bh, *Bl;
   float* C;
   CK(cudaMalloc(&Ah, a_rows * lda * 2)); CK(cudaMalloc(&Al, a_rows * lda * 2));
