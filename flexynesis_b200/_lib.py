@@ -88,7 +88,7 @@ SYMBOLS = [
     "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
     "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn", "fxn_gcn_fwd", "fxn_gcn_bwd",
-    "fxn_merge_col_stats", "fxn_debug_gemm_trace", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast",
+    "fxn_merge_col_stats", "fxn_debug_gemm_trace", "fxn_debug_gemm_cta_times", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast",
 ]
 
 

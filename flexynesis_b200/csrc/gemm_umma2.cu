@@ -124,6 +124,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 
 // ---- optional timeline of CTA 0 / CTA 1 (clock64 stamps), enabled with FXN_GEMM_TRACE=1; read by fxn_debug_gemm_trace ----
 __device__ long long g2_trace[2][16];
+__device__ unsigned long long g2_cta_time[2][512];     // %globaltimer at start / end of every CTA (trace mode)
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define G2_STAMP(slot)                                                        \
   do {                                                                        \
     if (p.trace && blockIdx.x < 2) g2_trace[blockIdx.x][slot] = clock64();    \
@@ -293,6 +299,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   float* stg_all = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * stage_bytes);
 
   if (threadIdx.x == 0) G2_STAMP(0);
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 512) g2_cta_time[0][blockIdx.x] = globaltimer_ns();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
     tma_prefetch_desc(&tmB_hi);
@@ -557,6 +564,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     g2_tmem_dealloc<CG>(tmem_base, p.tmem_cols);
   }
   if (threadIdx.x == 0) G2_STAMP(10);
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 512) g2_cta_time[1][blockIdx.x] = globaltimer_ns();
 }
 
 }  // namespace fxn
@@ -644,6 +652,12 @@ cudaError_t launch_gemm2(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (p.trace) {
+    int nclusters = -1;
+    cudaOccupancyMaxActiveClusters(&nclusters, gemm2_kernel<CG>, &cfg);
+    fprintf(stderr, "[gemm2] max co-resident clusters of %d CTAs at %d B smem: %d (launching %d)\n", CG, smem_bytes, nclusters,
+            groups);
+  }
   return cudaLaunchKernelEx(&cfg, gemm2_kernel<CG>, ta_hi, ta_lo, tb_hi, tb_lo, p);
 }
 
@@ -746,6 +760,22 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
 }  // namespace fxn
 
 // Debug: clock64 stamps of CTA 0 and CTA 1 of the last traced launch (FXN_GEMM_TRACE=1), relative to each CTA's start.
+// Debug: %globaltimer (ns) at start and end of CTA i of the last traced launch, relative to the earliest start
+// (-1 = CTA index not launched).
+extern "C" int fxn_debug_gemm_cta_times(long long* start_ns, long long* end_ns, int n) {
+  static unsigned long long h[2][512];
+  cudaError_t e = cudaMemcpyFromSymbol(h, fxn::g2_cta_time, sizeof(h));
+  if (e != cudaSuccess) return fxn::set_error(FXN_ERR_CUDA, "trace copy: %s", cudaGetErrorString(e));
+  if (n > 512) n = 512;
+  unsigned long long t0 = ~0ull;
+  for (int i = 0; i < n; ++i) if (h[0][i] != 0 && h[0][i] < t0) t0 = h[0][i];
+  for (int i = 0; i < n; ++i) {
+    start_ns[i] = h[0][i] ? static_cast<long long>(h[0][i] - t0) : -1;
+    end_ns[i] = h[0][i] ? static_cast<long long>(h[1][i] - t0) : -1;
+  }
+  return 0;
+}
+
 extern "C" int fxn_debug_gemm_trace(long long* out32) {
   long long h[2][16];
   cudaError_t e = cudaMemcpyFromSymbol(h, fxn::g2_trace, sizeof(h));

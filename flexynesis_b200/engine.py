@@ -23,6 +23,42 @@ def pad128(n: int) -> int:
     return (int(n) + 127) // 128 * 128
 
 
+def concurrent_tile_widths(rows: int, widths: Sequence[int], depths: Sequence[int], sms: int = 148) -> List[int]:
+    """Tile widths (fxn_gemm block_n) for the first-layer GEMMs of several modalities that run as PARALLEL graph branches.
+    Left alone, each GEMM plans for the whole chip (128-wide tiles on ~128 SMs) and the two launches queue behind each
+    other; their 128-wide tiles are also bound by shared-memory ingest (~42 B/clk/SM measured: 48 KB per k-block against
+    768 MMA cycles). Wider tiles on fewer SMs are MMA-bound and let the branches really overlap. Model per k-block of one
+    CTA pair tile [256 x bn] with the 3-term split: MMA 6*bn cycles, ingest (32768 + 128*bn) / 42 cycles; the choice
+    minimises the slowest branch subject to all CTAs being co-resident (one CTA per SM). Returns 0 (= library default)
+    when there is a single branch."""
+    if len(widths) < 2:
+        return [0] * len(widths)
+    import itertools
+    mt = (rows + 255) // 256
+    cands = []
+    for h, d in zip(widths, depths):
+        opts = []
+        for bn in range(32, 257, 32):
+            tn = (h + bn - 1) // bn
+            if tn > 1 and (tn - 1) * bn >= h:
+                continue
+            kb = (d + 63) // 64
+            t = kb * max(6.0 * bn, (32768.0 + 128.0 * bn) / 42.0) + 9000.0 + 1450.0 * (bn // 32)
+            opts.append((bn, 2 * mt * tn, t))
+        cands.append(opts)
+    best, best_t = None, None
+    for combo in itertools.product(*cands):
+        ctas = sum(c[1] for c in combo)
+        if ctas > sms:
+            continue
+        t = max(c[2] for c in combo)
+        if best_t is None or t < best_t or (t == best_t and ctas < sum(c[1] for c in best)):
+            best, best_t = combo, t
+    if best is None:
+        return [0] * len(widths)
+    return [c[0] for c in best]
+
+
 # ----------------------------------------------------------------------------------------------------
 # flat parameter arena
 # ----------------------------------------------------------------------------------------------------
@@ -570,6 +606,7 @@ class TrunkEngine(EngineBase):
         B, Bp, R, G = ws["B"], ws["Bp"], ws["R"], self.G
         mt = L.stat_tiles(Bp)
         tags = [""] if G == 1 else ["anchor.", "positive.", "negative."]
+        bns = concurrent_tile_widths(R, self.h, self.d) if self.parallel_encoders else [0] * self.n
         self._fork()
         for i in range(self.n):
           with torch.cuda.stream(self._stream_for(i)):
@@ -578,7 +615,7 @@ class TrunkEngine(EngineBase):
               use_epi_stats = train and G == 1
               L.gemm(R, h, self.d[i], ws["X"][i], 0, self.wp(self.w1[i]), 0, C_ptr=ws["Z"][i].data_ptr(), ldc=hp,
                      bias=a.p(f"encoders.{i}.layer_1.bias"),
-                     colstats=ws["partials"][i].data_ptr() if use_epi_stats else None, stats_mode=2)
+                     colstats=ws["partials"][i].data_ptr() if use_epi_stats else None, stats_mode=2, block_n=bns[i])
               for g in range(G):
                   r0 = g * Bp
                   if train and G > 1:

@@ -86,6 +86,9 @@ int fxn_gemm(const fxn_gemm_desc* d, void* stream);
 /* Debug aid: with FXN_GEMM_TRACE=1 in the environment the persistent kernel stamps clock64 at its pipeline milestones
  * for CTA 0 and CTA 1; this copies the 2 x 16 stamps (cycles since CTA start, -1 = not reached) of the last launch. */
 int fxn_debug_gemm_trace(long long* out32);
+/* Same mode: %globaltimer (ns, relative to the earliest CTA start) at entry and exit of CTAs 0..n-1 (n <= 512) of the
+ * last traced launch -- shows scheduling waves and stragglers. */
+int fxn_debug_gemm_cta_times(long long* start_ns, long long* end_ns, int n);
 int fxn_gemm_stat_tiles(int M);
 
 /* ---- BatchNorm1d (+ activation + dropout) ----

@@ -216,6 +216,13 @@ static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn
                                "all tiles stored", "end"};
       for (int i = 0; i < 11; ++i) printf("  trace %-30s cta0 %8lld  cta1 %8lld cycles\n", names[i], t[i], t[16 + i]);
     }
+    long long st[512], en[512];
+    if (fxn_debug_gemm_cta_times(st, en, 512) == 0) {
+      printf("  cta start/end us:");
+      for (int i = 0; i < 160; i += 2)
+        if (st[i] >= 0) printf(" %d:%.1f-%.1f", i, st[i] * 1e-3, en[i] * 1e-3);
+      printf("\n");
+    }
   }
   cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl); cudaFree(C);
 }
