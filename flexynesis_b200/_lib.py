@@ -33,6 +33,7 @@ class GemmDesc(C.Structure):
         ("mse_x", C.c_void_p), ("ldx", c_ll), ("mse_acc", C.c_void_p),
         ("gauss_ra", C.c_void_p), ("gauss_rb", C.c_void_p), ("gauss_inv", C.c_float),
         ("stats_alpha", C.c_float), ("stats_alpha_dev", C.c_void_p),
+        ("outputs_prezeroed", C.c_int),
     ]
 
 
@@ -63,7 +64,7 @@ class BnBwdDesc(C.Structure):
         ("dV", C.c_void_p), ("ldd", c_ll),
         ("dv_hi", C.c_void_p), ("dv_lo", C.c_void_p), ("ldp", c_ll),
         ("grad_scale", C.c_float), ("accumulate_affine", C.c_int),
-        ("stat_rows", c_ll), ("phase", C.c_int),
+        ("stat_rows", c_ll), ("prezeroed", C.c_int), ("phase", C.c_int),
     ]
 
 
@@ -177,7 +178,7 @@ def split_planes(src: torch.Tensor, dst: Planes) -> None:
 def gemm(M, N, K, a: Planes, a_mn, b: Planes, b_mn, *, C_ptr=None, ldc=0, bias=None, out: Planes = None,
          colstats=None, stats_mode=0, splitk=0, nterms=3, block_n=0, epi_act=0, accumulate=False, alpha=0.0,
          alpha_dev=None, mse_x=None, ldx=0, mse_acc=None, gauss_ra=None, gauss_rb=None, gauss_inv=0.0,
-         stats_alpha=0.0, stats_alpha_dev=None) -> None:
+         stats_alpha=0.0, stats_alpha_dev=None, prezeroed=False) -> None:
     d = GemmDesc()
     d.M, d.N, d.K = int(M), int(N), int(K)
     d.a_hi, d.a_lo, d.lda, d.a_mn_major = a.hi_ptr, a.lo_ptr, a.ld, int(a_mn)
@@ -194,6 +195,7 @@ def gemm(M, N, K, a: Planes, a_mn, b: Planes, b_mn, *, C_ptr=None, ldc=0, bias=N
     d.mse_x, d.ldx, d.mse_acc = mse_x, int(ldx), mse_acc
     d.gauss_ra, d.gauss_rb, d.gauss_inv = gauss_ra, gauss_rb, gauss_inv
     d.stats_alpha, d.stats_alpha_dev = stats_alpha, stats_alpha_dev
+    d.outputs_prezeroed = int(prezeroed)
     check(lib.fxn_gemm(C.byref(d), C.c_void_p(stream())), "fxn_gemm")
 
 

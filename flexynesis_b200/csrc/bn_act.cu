@@ -517,8 +517,11 @@ extern "C" int fxn_bn_act_bwd(const fxn_bn_bwd_desc* d, void* stream_) {
   const int width = a.dv_hi ? ((a.cols + 7) & ~7) : a.cols;
   a.rpb = bn_rows_per_block(a.rows, ceil_div(width, BN_COLS));
   if (d->phase != 2) {
-    cudaError_t e = cudaMemsetAsync(a.sums, 0, sizeof(float) * 2 * a.pcols, stream);
-    if (e == cudaSuccess && a.dbias) e = cudaMemsetAsync(a.dbias, 0, sizeof(float) * a.pcols, stream);
+    cudaError_t e = cudaSuccess;
+    if (!d->prezeroed) {
+      e = cudaMemsetAsync(a.sums, 0, sizeof(float) * 2 * a.pcols, stream);
+      if (e == cudaSuccess && a.dbias) e = cudaMemsetAsync(a.dbias, 0, sizeof(float) * a.pcols, stream);
+    }
     if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "bn_bwd memset: %s", cudaGetErrorString(e));
     dim3 grid(ceil_div(a.cols, BN_COLS), ceil_div(a.rows, a.rpb));
     bn_bwd_reduce_kernel<<<grid, BN_THREADS, 0, stream>>>(a);

@@ -480,11 +480,11 @@ extern "C" int fxn_gemm(const fxn_gemm_desc* d, void* stream_) {
     if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  if (p.stats_mode == 3) {   // plain column sums are accumulated with atomics: zero the target first
+  if (p.stats_mode == 3 && !d->outputs_prezeroed) {   // plain column sums are accumulated with atomics: zero the target first
     cudaError_t e = cudaMemsetAsync(d->colstats, 0, sizeof(float) * d->N, stream);
     if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "colsum memset: %s", cudaGetErrorString(e));
   }
-  if (splitk > 1) {
+  if (splitk > 1 && !d->outputs_prezeroed) {
     cudaError_t e = cudaMemset2DAsync(d->C, d->ldc * sizeof(float), 0, d->N * sizeof(float), d->M, stream);
     if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "split-K memset: %s", cudaGetErrorString(e));
   }

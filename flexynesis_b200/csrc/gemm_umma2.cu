@@ -739,11 +739,11 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
     ta_lo = ta_hi;
     tb_lo = tb_hi;
   }
-  if (p.stats_mode == 3) {
+  if (p.stats_mode == 3 && !d->outputs_prezeroed) {
     cudaError_t e = cudaMemsetAsync(d->colstats, 0, sizeof(float) * d->N, stream);
     if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "colsum memset: %s", cudaGetErrorString(e));
   }
-  if (p.streamk) {
+  if (p.streamk && !d->outputs_prezeroed) {
     cudaError_t e = cudaMemset2DAsync(d->C, d->ldc * sizeof(float), 0, d->N * sizeof(float), d->M, stream);
     if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "stream-K memset: %s", cudaGetErrorString(e));
   }

@@ -332,7 +332,9 @@ class HeadsBlock:
         return fptr(ws["out"], self.n_losses + 2 + self.loss_names.index(name))
 
     # ---- backward: fills head grads and writes dF (planes, optional fp32 accumulate target) ----
-    def backward(self, ws, Fp: Planes, B: int, y, masks, dF: Planes, dF_f32=None, dbias_ptr=None, accumulate=False):
+    def backward(self, ws, Fp: Planes, B: int, y, masks, dF: Planes, dF_f32=None, dbias_ptr=None, accumulate=False,
+                 prezeroed: bool = False):
+        """prezeroed: the caller zeroed the gradient arena and ws['sums'] for this step already (no memsets queued)."""
         eng, a = self.eng, self.eng.arena
         if not self.vars:
             return False
@@ -357,17 +359,20 @@ class HeadsBlock:
                             mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
                             seed=eng.seed + 7919 * (i + 1), seed_dev=eng.arena.step.data_ptr(), pre_act=0,
                             sums=ws["sums"][i], dgamma=a.view(f"MLPs.{v}.batchnorm.weight", a.grad),
-                            dbeta=a.view(f"MLPs.{v}.batchnorm.bias", a.grad), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+                            dbeta=a.view(f"MLPs.{v}.batchnorm.bias", a.grad), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld,
+                            prezeroed=prezeroed)
         # dF [B x L] = dZh_cat * W1cat   (+ column sums -> bias gradient of whatever produced F): the critical path
         ev = eng._mark()
         L.gemm(B, self.L, self.width, ws["dZh"], 0, self.w1_planes(), 1,
                C_ptr=None if dF_f32 is None else dF_f32.data_ptr(), ldc=0 if dF_f32 is None else dF_f32.stride(0),
-               out=dF, colstats=dbias_ptr, stats_mode=3 if dbias_ptr is not None else 0, accumulate=accumulate)
+               out=dF, colstats=dbias_ptr, stats_mode=3 if dbias_ptr is not None else 0, accumulate=accumulate,
+               prezeroed=prezeroed)
 
         def wgrads():
             for i, v in enumerate(self.vars):      # dW1_v [sh x L] = dZh_v^T * F
                 dz = ws["dZh"].cols_view(i * self.shp, self.sh)
-                L.gemm(self.sh, self.L, B, dz, 1, Fp, 1, C_ptr=a.g(f"MLPs.{v}.layer_1.weight"), ldc=self.L, splitk=-1)
+                L.gemm(self.sh, self.L, B, dz, 1, Fp, 1, C_ptr=a.g(f"MLPs.{v}.layer_1.weight"), ldc=self.L, splitk=-1,
+                       prezeroed=prezeroed)
         eng._aux_run(len(eng.aux) - 1, wgrads, after=ev)       # joined by the engine at the end of its backward pass
         return True
 
@@ -472,14 +477,15 @@ class EngineBase:
         kw.update(partials=allrec.data_ptr(), ntiles=s.world, tile_rows=rows, partials_ld=cols, stat_rows=s.world * rows)
         L.bn_fwd(**kw)
 
-    def bn_backward(self, *, sums: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor, accumulate_affine: int = 0, **kw):
+    def bn_backward(self, *, sums: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor, accumulate_affine: int = 0,
+                    prezeroed: bool = False, **kw):
         """fxn_bn_act_bwd; `sums` is the [2 * cols] scratch tensor, dgamma / dbeta are views of the gradient arena. With
         `self.sync`: column reductions over the local rows (phase 1; they ARE this rank's share of dgamma / dbeta), sum
         all-reduce, apply pass with the global sums and the global row count (phase 2)."""
         s = self.sync
         if s is None:
             L.bn_bwd(sums=sums.data_ptr(), dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(),
-                     accumulate_affine=accumulate_affine, **kw)
+                     accumulate_affine=accumulate_affine, prezeroed=int(prezeroed), **kw)
             return
         cols = int(kw["cols"])
         flat = sums.view(-1)
@@ -587,6 +593,7 @@ class TrunkEngine(EngineBase):
         ws["dF"] = torch.zeros(R, self.Lp, device=dev)          # fp32 copy (triplet adds its own gradient here)
         ws["rowloss"] = torch.zeros(B, device=dev)
         ws["heads"] = self.heads.workspace(B)
+        ws["_zero"] = list(ws["sums"]) + [ws["heads"]["sums"]]     # accumulation scratch zeroed once per step
         self.ws[B] = ws
         return ws
 
@@ -640,7 +647,7 @@ class TrunkEngine(EngineBase):
                    ldc=self.Lp, bias=a.p("fusion_block.bias"), out=ws["F_p"])
 
     # -- backward of the trunk given dF planes (all groups) --
-    def trunk_backward(self, ws, masks):
+    def trunk_backward(self, ws, masks, pz: bool = False):
         a, model = self.arena, self.model
         B, Bp, R, G = ws["B"], ws["Bp"], ws["R"], self.G
         tags = [""] if G == 1 else ["anchor.", "positive.", "negative."]
@@ -657,16 +664,17 @@ class TrunkEngine(EngineBase):
                   ev = self._mark()
                   # dE_i = dF * Wf[:, iL:(i+1)L]   (+ column sums -> d layer_out.bias)
                   L.gemm(R, Lt, Lt, ws["dF_p"], 0, self.wf_planes(i), 1, out=dE,
-                         colstats=a.g(f"encoders.{i}.layer_out.bias") if has_b2 else None, stats_mode=3)
+                         colstats=a.g(f"encoders.{i}.layer_out.bias") if has_b2 else None, stats_mode=3, prezeroed=pz)
                   # dWf[:, iL:(i+1)L] = dF^T * E_i        (beside it: needs dF only)
                   self._aux_run(i, lambda i=i, E_p=E_p: L.gemm(
                       Lt, Lt, R, ws["dF_p"], 1, E_p, 1, C_ptr=fptr(a.grad, a.offset["fusion_block.weight"] + i * Lt),
-                      ldc=self.n * Lt, splitk=-1), after=ev)
+                      ldc=self.n * Lt, splitk=-1, prezeroed=pz), after=ev)
               # dD_i = dE_i * W2_i (critical path) ; dW2_i = dE_i^T * D_i (beside it)
               ev = self._mark()
               L.gemm(R, h, Lt, dE, 0, self.wp(self.w2[i]), 1, C_ptr=ws["dD"][i].data_ptr(), ldc=hp)
               self._aux_run(i, lambda i=i, dE=dE, h=h: L.gemm(
-                  Lt, h, R, dE, 1, ws["D"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_out.weight"), ldc=h, splitk=-1), after=ev)
+                  Lt, h, R, dE, 1, ws["D"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_out.weight"), ldc=h, splitk=-1,
+                  prezeroed=pz), after=ev)
               for g in range(G):
                   r0 = g * Bp
                   mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
@@ -682,10 +690,10 @@ class TrunkEngine(EngineBase):
                                    dgamma=a.view(f"encoders.{i}.batchnorm.weight", a.grad),
                                    dbeta=a.view(f"encoders.{i}.batchnorm.bias", a.grad),
                                    accumulate_affine=0 if first else 1,   # affine grads add up over the three triplet passes
-                                   dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+                                   dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld, prezeroed=pz)
               # dW1_i = dZ_i^T * X_i
               L.gemm(h, self.d[i], R, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_1.weight"),
-                     ldc=self.d[i], splitk=-1)
+                     ldc=self.d[i], splitk=-1, prezeroed=pz)
               self._aux_join(i)
         self._join()
         self._aux_join(len(self.aux) - 1)          # the heads' weight gradients
@@ -701,6 +709,12 @@ class TrunkEngine(EngineBase):
         self.ensure_fresh()
         self.stage_inputs(ws, x_groups)
         hw["acc"].zero_()
+        # every gradient accumulator (stream-K wgrads, column-sum bias gradients, BatchNorm reduction scratch) is zeroed
+        # ONCE here, on a stream beside the forward pass, instead of by ~15 small memset nodes on the backward critical path
+        pz = self.sync is None and self.parallel_encoders
+        zk = len(self.aux) - 1
+        if pz:
+            self._aux_run(zk, lambda: (self.arena.grad.zero_(), torch._foreach_zero_(ws["_zero"])))
         self.trunk_forward(ws, True, masks)
         Fa = ws["F_p"].rows_view(0, B)
         self.heads.forward(hw, Fa, B, y, True, masks)
@@ -717,16 +731,18 @@ class TrunkEngine(EngineBase):
             dbias = a.g("encoders.0.layer_out.bias")
         else:
             dbias = None
+        if pz:
+            self._aux_join(zk)
         if self.G == 1:
-            self.heads.backward(hw, Fa, B, y, masks, ws["dF_p"].rows_view(0, B), None, dbias)
+            self.heads.backward(hw, Fa, B, y, masks, ws["dF_p"].rows_view(0, B), None, dbias, prezeroed=pz)
         else:
             Bp, Lp = ws["Bp"], self.Lp
-            self.heads.backward(hw, Fa, B, y, masks, ws["dF_p"].rows_view(0, B), ws["dF"], dbias)
+            self.heads.backward(hw, Fa, B, y, masks, ws["dF_p"].rows_view(0, B), ws["dF"], dbias, prezeroed=pz)
             L.triplet_bwd(ws["F"].data_ptr(), fptr(ws["F"], Bp * Lp), fptr(ws["F"], 2 * Bp * Lp), Lp, B, self.latent,
                           ws["rowloss"].data_ptr(), self.heads.weight_ptr(hw, "triplet_loss"), ws["dF"].data_ptr(),
                           fptr(ws["dF"], Bp * Lp), fptr(ws["dF"], 2 * Bp * Lp), Lp, True)
             L.split_planes(ws["dF"][:, :self.latent], ws["dF_p"])
-        self.trunk_backward(ws, masks)
+        self.trunk_backward(ws, masks, pz)
         return ws
 
     def evaluate(self, x_groups, y=None, train_mode: bool = False, masks=None):

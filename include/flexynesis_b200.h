@@ -81,6 +81,10 @@ typedef struct fxn_gemm_desc {
   const float* gauss_ra; const float* gauss_rb; float gauss_inv;
   /* stats_mode 3 column sums are multiplied by stats_alpha (0 means 1) * *stats_alpha_dev (if not NULL) */
   float stats_alpha; const float* stats_alpha_dev;
+  /* the caller has already zeroed every accumulation target of this call (a stream-K / split-K C and the stats_mode 3
+   * column sums): the library then queues no memset in front of the kernel (the engine zeroes its whole gradient arena
+   * once per step, beside the forward pass) */
+  int outputs_prezeroed;
 } fxn_gemm_desc;
 int fxn_gemm(const fxn_gemm_desc* d, void* stream);
 /* Debug aid: with FXN_GEMM_TRACE=1 in the environment the persistent kernel stamps clock64 at its pipeline milestones
@@ -139,6 +143,7 @@ typedef struct fxn_bn_bwd_desc {
   float grad_scale;      /* multiplies dOut; 0 means 1 */
   int accumulate_affine; /* dgamma/dbeta += instead of = (a module applied several times per step) */
   long long stat_rows;   /* rows the forward statistics covered (0 = rows); see fxn_bn_fwd_desc */
+  int prezeroed;         /* `sums` and `dbias` are already zero: queue no memsets */
   int phase;             /* 0: whole backward. 1: only the column reductions into `sums` (sum g, sum g*xhat over this
                             call's rows). 2: only the apply pass, reading `sums` as given -- a data-parallel caller
                             sum-all-reduces `sums` between phase 1 and phase 2 (SyncBN backward) */
