@@ -89,7 +89,7 @@ SYMBOLS = [
     "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
     "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn", "fxn_gcn_fwd", "fxn_gcn_bwd",
-    "fxn_merge_col_stats", "fxn_debug_gemm_trace", "fxn_debug_gemm_cta_times", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast",
+    "fxn_merge_col_stats", "fxn_node_lin_fwd", "fxn_node_lin_bwd", "fxn_debug_gemm_trace", "fxn_debug_gemm_cta_times", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast",
 ]
 
 
@@ -335,6 +335,16 @@ def gcn_bwd(X, dO, B, N, Fin, emb, csr_in, csr_out, W, dW, dbias, dX) -> None:
                           C.c_void_p(csr_in[2].data_ptr()), C.c_void_p(csr_out[0].data_ptr()),
                           C.c_void_p(csr_out[1].data_ptr()), C.c_void_p(csr_out[2].data_ptr()), C.c_void_p(W),
                           C.c_void_p(dW), C.c_void_p(dbias), C.c_void_p(dX), C.c_void_p(stream())), "fxn_gcn_bwd")
+
+
+def node_lin_fwd(X, B, N, Fin, Wr, emb, O, partials) -> None:
+    check(lib.fxn_node_lin_fwd(C.c_void_p(X), C.c_int(B), C.c_int(N), C.c_int(Fin), C.c_void_p(Wr), C.c_int(emb),
+                               C.c_void_p(O), C.c_void_p(partials), C.c_void_p(stream())), "fxn_node_lin_fwd")
+
+
+def node_lin_bwd(X, dO, B, N, Fin, emb, Wr, dWr, dX) -> None:
+    check(lib.fxn_node_lin_bwd(C.c_void_p(X), C.c_void_p(dO), C.c_int(B), C.c_int(N), C.c_int(Fin), C.c_int(emb),
+                               C.c_void_p(Wr), C.c_void_p(dWr), C.c_void_p(dX), C.c_void_p(stream())), "fxn_node_lin_bwd")
 
 
 def merge_col_stats(partials, ntiles, tile_rows, rows, cols, pld, merged) -> None:

@@ -111,8 +111,58 @@ class GCNConv(nn.Module):
         return torch.zeros_like(h).index_add_(-2, dst, h[..., src, :] * w[:, None]) + self.bias
 
 
+class _RootConv(nn.Module):
+    """Shared torch formulation of torch_geometric's GraphConv / SAGEConv on batched dense x [B, N, F] with one edge_index
+    (un-vendored third party; algorithms restated from their published semantics, oracle/restatement.py:graph_conv /
+    sage_conv): neighbour aggregate through one Linear with bias, the node's own features through a bias-free Linear."""
+    MEAN = False
+    NEIGH, ROOT = "lin_rel", "lin_root"
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        setattr(self, self.NEIGH, nn.Linear(in_channels, out_channels, bias=True))
+        setattr(self, self.ROOT, nn.Linear(in_channels, out_channels, bias=False))
+
+    @property
+    def neigh(self) -> nn.Linear:
+        return getattr(self, self.NEIGH)
+
+    @property
+    def root(self) -> nn.Linear:
+        return getattr(self, self.ROOT)
+
+    @classmethod
+    def edge_weights(cls, edge_index: torch.Tensor, num_nodes: int):
+        """(src, dst, w): the directed list as given; w = 1 (sum) or 1 / in-degree of the destination (mean)."""
+        src, dst = edge_index[0].long(), edge_index[1].long()
+        w = torch.ones(dst.numel(), dtype=torch.float32, device=edge_index.device)
+        if cls.MEAN:
+            deg = torch.zeros(num_nodes, device=edge_index.device).scatter_add_(0, dst, w)
+            w = 1.0 / deg.clamp_min(1.0)[dst]
+        return src, dst, w
+
+    def forward(self, x, edge_index):
+        src, dst, w = self.edge_weights(edge_index, x.shape[-2])
+        agg = torch.zeros_like(x).index_add_(-2, dst, x[..., src, :] * w[:, None])
+        return self.neigh(agg) + self.root(x)
+
+
+class GraphConv(_RootConv):
+    """GraphConv(in, out, aggr='add'): state keys lin_rel.{weight,bias}, lin_root.weight (PyG's)."""
+
+
+class SAGEConv(_RootConv):
+    """SAGEConv(in, out, aggr='mean', root_weight=True): state keys lin_l.{weight,bias}, lin_r.weight (PyG's)."""
+    MEAN = True
+    NEIGH, ROOT = "lin_l", "lin_r"
+
+
+CONVS = {"GCN": GCNConv, "GC": GraphConv, "SAGE": SAGEConv}
+
+
 class flexGCN(nn.Module):
-    """num_convs x (GCNConv -> BatchNorm1d over B*N rows -> act -> Dropout(0.2)) -> flatten -> Linear(N*emb, out)."""
+    """num_convs x (conv -> BatchNorm1d over B*N rows -> act -> Dropout(0.2)) -> flatten -> Linear(N*emb, out), conv in
+    {GCN, GC, SAGE} (flexynesis/modules.py:195-262; the reference's default is GC)."""
 
     def __init__(self, node_count, node_feature_count, node_embedding_dim, output_dim, num_convs=2, dropout_rate=0.2,
                  conv="GC", act="relu"):
@@ -121,16 +171,17 @@ class flexGCN(nn.Module):
             raise ValueError("Invalid activation function string. Choose from ", list(ACTIVATIONS))
         if conv not in ("GCN", "GAT", "SAGE", "GC"):
             raise ValueError("Unknown convolution type. Choose one of: ", ["GCN", "GAT", "SAGE", "GC"])
-        if conv != "GCN":
-            raise NotImplementedError(f"conv='{conv}': the B200 engine implements GCN (SURVEY.md section 8, row f3 lists "
-                                      "GC/SAGE/GAT as next)")
+        if conv == "GAT":
+            raise NotImplementedError("conv='GAT': the B200 engine implements GCN, GC (GraphConv) and SAGE; attention "
+                                      "convolutions are not built (DESIGN.md, out of scope)")
+        self.conv_name = conv
         self.act_name, self.dropout_rate = act, dropout_rate
         self.act = {"relu": nn.ReLU(), "sigmoid": nn.Sigmoid(), "leakyrelu": nn.LeakyReLU(), "tanh": nn.Tanh(),
                     "gelu": nn.GELU()}[act]
         self.convs, self.bns = nn.ModuleList(), nn.ModuleList()
         self.dropout = nn.Dropout(dropout_rate)
         for k in range(num_convs):
-            self.convs.append(GCNConv(node_feature_count if k == 0 else node_embedding_dim, node_embedding_dim))
+            self.convs.append(CONVS[conv](node_feature_count if k == 0 else node_embedding_dim, node_embedding_dim))
             self.bns.append(nn.BatchNorm1d(node_embedding_dim))
         self.fc = nn.Linear(node_embedding_dim * node_count, output_dim)
 

@@ -1046,28 +1046,44 @@ class VAEEngine(EngineBase):
 # ----------------------------------------------------------------------------------------------------
 # GNN (flexGCN with GCN convolutions)
 # ----------------------------------------------------------------------------------------------------
-def build_gcn_csr(edge_index: torch.Tensor, num_nodes: int, device):
-    """gcn_norm of torch_geometric (add the missing self loops, in-degree on the directed list as given,
-    w = deg_src^-1/2 * deg_dst^-1/2) as two CSRs: by destination (forward / weight gradient) and by source (input
-    gradient). Built once per model; edges of one row keep their edge_index order so sums are reproducible."""
+def build_gcn_csr(edge_index: torch.Tensor, num_nodes: int, device, conv: str = "GCN"):
+    """The graph of a flexGCN layer as two CSRs: by destination (forward / weight gradient) and by source (input
+    gradient), built once per model; edges of one row keep their edge_index order so sums are reproducible.
+      GCN : gcn_norm of torch_geometric (add the missing self loops, in-degree on the directed list as given,
+            w = deg_src^-1/2 * deg_dst^-1/2);
+      GC  : GraphConv's sum over the directed list as given, w = 1;
+      SAGE: SAGEConv's mean, w = 1 / in-degree of the destination."""
     ei = edge_index.to("cpu", torch.long)
     src, dst = ei[0], ei[1]
-    looped = torch.zeros(num_nodes, dtype=torch.bool)
-    looped[src[src == dst]] = True
-    extra = torch.nonzero(~looped).flatten()
-    src, dst = torch.cat([src, extra]), torch.cat([dst, extra])
-    deg = torch.zeros(num_nodes, dtype=torch.float32).scatter_add_(0, dst, torch.ones(dst.numel()))
-    dinv = deg.pow(-0.5)
-    dinv[torch.isinf(dinv)] = 0
-    w = dinv[src] * dinv[dst]
+    if conv == "GCN":
+        looped = torch.zeros(num_nodes, dtype=torch.bool)
+        looped[src[src == dst]] = True
+        extra = torch.nonzero(~looped).flatten()
+        src, dst = torch.cat([src, extra]), torch.cat([dst, extra])
+        deg = torch.zeros(num_nodes, dtype=torch.float32).scatter_add_(0, dst, torch.ones(dst.numel()))
+        dinv = deg.pow(-0.5)
+        dinv[torch.isinf(dinv)] = 0
+        w = dinv[src] * dinv[dst]
+    elif conv == "GC":
+        w = torch.ones(dst.numel(), dtype=torch.float32)
+    elif conv == "SAGE":
+        deg = torch.zeros(num_nodes, dtype=torch.float32).scatter_add_(0, dst, torch.ones(dst.numel()))
+        w = 1.0 / deg.clamp_min(1.0)[dst]
+    else:
+        raise ValueError(f"unsupported convolution {conv!r}")
 
     def csr(key, other):
         order = torch.sort(key, stable=True).indices
         counts = torch.bincount(key, minlength=num_nodes)
         rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64)
         rowptr[1:] = torch.cumsum(counts, 0)
-        return (rowptr.to(device, torch.int32), other[order].to(device, torch.int32).contiguous(),
-                w[order].to(device, torch.float32).contiguous())
+        col = other[order].to(device, torch.int32).contiguous()
+        if col.numel() == 0:                      # an edgeless graph still needs valid pointers
+            col = torch.zeros(1, dtype=torch.int32, device=device)
+        wv = w[order].to(device, torch.float32).contiguous()
+        if wv.numel() == 0:
+            wv = torch.zeros(1, dtype=torch.float32, device=device)
+        return (rowptr.to(device, torch.int32), col, wv)
 
     return csr(dst, src), csr(src, dst)
 
@@ -1080,14 +1096,18 @@ class GNNEngine(EngineBase):
         super().__init__(model, device)
         enc = model.encoders[0]
         self.K = len(enc.convs)
-        self.emb = enc.convs[0].lin.out_features
-        self.F = enc.convs[0].lin.in_features
+        self.conv = getattr(enc, "conv_name", "GCN")
+        # parameter names of the neighbour transform (weight, bias) and of the root transform (GC / SAGE only)
+        self.pn = {"GCN": ("lin.weight", "bias", None), "GC": ("lin_rel.weight", "lin_rel.bias", "lin_root.weight"),
+                   "SAGE": ("lin_l.weight", "lin_l.bias", "lin_r.weight")}[self.conv]
+        w0 = self.arena.shape[f"encoders.0.convs.0.{self.pn[0]}"]
+        self.emb, self.F = int(w0[0]), int(w0[1])
         self.N = enc.fc.in_features // self.emb
         self.p_drop = float(enc.dropout_rate)
         from .containers import ACTIVATIONS
         self.act = ACTIVATIONS[enc.act_name]
         self.wfc = self.wplanes.add_matrix("encoders.0.fc.weight")
-        self.csr_in, self.csr_out = build_gcn_csr(model.edge_index, self.N, self.device)
+        self.csr_in, self.csr_out = build_gcn_csr(model.edge_index, self.N, self.device, self.conv)
         self._finish_init(0)
 
     def workspace(self, B: int) -> dict:
@@ -1126,9 +1146,12 @@ class GNNEngine(EngineBase):
         xin = self._conv_inputs(ws)
         for k in range(K):
             fin = self.F if k == 0 else emb
+            pw, pb, pr = (f"encoders.0.convs.{k}.{n}" if n else None for n in self.pn)
+            part = ws["partials"][k].data_ptr() if train else None
             L.gcn_fwd(xin[k].data_ptr(), B, N, fin, self.csr_in[0].data_ptr(), self.csr_in[1].data_ptr(),
-                      self.csr_in[2].data_ptr(), a.p(f"encoders.0.convs.{k}.lin.weight"), a.p(f"encoders.0.convs.{k}.bias"),
-                      emb, ws["O"][k].data_ptr(), ws["partials"][k].data_ptr() if train else None)
+                      self.csr_in[2].data_ptr(), a.p(pw), a.p(pb), emb, ws["O"][k].data_ptr(), None if pr else part)
+            if pr:      # GraphConv / SAGEConv: + root transform of the node's own features, then the statistics of O
+                L.node_lin_fwd(xin[k].data_ptr(), B, N, fin, a.p(pr), emb, ws["O"][k].data_ptr(), part)
             if train:
                 L.merge_col_stats(ws["partials"][k].data_ptr(), B, N, rows, emb, emb, ws["merged"][k].data_ptr())
             mask = None if masks is None else masks.get(f"encoders.0.dropout.{k}")
@@ -1185,9 +1208,12 @@ class GNNEngine(EngineBase):
                              seed_dev=a.step.data_ptr(), pre_act=0, sums=ws["sums"][k],
                              dgamma=a.view(f"encoders.0.bns.{k}.weight", a.grad),
                              dbeta=a.view(f"encoders.0.bns.{k}.bias", a.grad), dV=ws["dO"].data_ptr(), ldd=emb)
+            pw, pb, pr = (f"encoders.0.convs.{k}.{n}" if n else None for n in self.pn)
+            dX = ws["dD"].data_ptr() if k > 0 else None
             L.gcn_bwd(xin[k].data_ptr(), ws["dO"].data_ptr(), B, N, fin, emb, self.csr_in, self.csr_out,
-                      a.p(f"encoders.0.convs.{k}.lin.weight"), a.g(f"encoders.0.convs.{k}.lin.weight"),
-                      a.g(f"encoders.0.convs.{k}.bias"), ws["dD"].data_ptr() if k > 0 else None)
+                      a.p(pw), a.g(pw), a.g(pb), dX)
+            if pr:
+                L.node_lin_bwd(xin[k].data_ptr(), ws["dO"].data_ptr(), B, N, fin, emb, a.p(pr), a.g(pr), dX)
         self._aux_join(len(self.aux) - 1)          # the heads' weight gradients
         return ws
 

@@ -223,6 +223,15 @@ int fxn_gcn_fwd(const float* X, int B, int N, int Fin, const int* rowptr, const 
 int fxn_gcn_bwd(const float* X, const float* dO, int B, int N, int Fin, int emb, const int* rowptr_in, const int* col_in,
                 const float* w_in, const int* rowptr_out, const int* col_out, const float* w_out, const float* W,
                 float* dW, float* dbias, float* dX, void* stream);
+/* Root-weight term of torch_geometric's GraphConv / SAGEConv as flexGCN calls them (flexynesis/modules.py:221-226, :254):
+ *   GraphConv: lin_rel(sum_{u->v} x_u) + lin_root(x_v) ;  SAGEConv: lin_l(mean_{u->v} x_u) + lin_r(x_v).
+ * The neighbour term runs through fxn_gcn_fwd / fxn_gcn_bwd with edge weights 1 (GraphConv) or 1/in-degree (SAGEConv) and
+ * no added self loops; these two calls add the per-node term with Wr = lin_root.weight / lin_r.weight [emb x Fin]:
+ *   fwd: O[b, v, :] += Wr X[b, v, :], then `partials` (optional, [B][2][emb]) = per-sample (sum, M2) of the finished O;
+ *   bwd: dWr = sum_{b,v} dO[b,v]^T X[b,v] (zeroed by the call) and, when dX != NULL, dX[b, v, :] += Wr^T dO[b, v, :]. */
+int fxn_node_lin_fwd(const float* X, int B, int N, int Fin, const float* Wr, int emb, float* O, float* partials, void* stream);
+int fxn_node_lin_bwd(const float* X, const float* dO, int B, int N, int Fin, int emb, const float* Wr, float* dWr, float* dX,
+                     void* stream);
 /* Chan-merge [ntiles][2][pld] column partials (tile_rows rows per tile) into one record merged[2][cols] = (sum, M2),
  * which fxn_bn_act_fwd accepts as partials with ntiles = 1, tile_rows = rows. */
 int fxn_merge_col_stats(const float* partials, int ntiles, int tile_rows, long long rows, int cols, int pld,

@@ -213,15 +213,40 @@ def gcn_conv(P, prefix: str, x: Tensor, edge_index: Tensor) -> Tensor:
     return out + P[prefix + ".bias"]
 
 
+def graph_conv(P, prefix: str, x: Tensor, edge_index: Tensor) -> Tensor:
+    """torch_geometric.nn.GraphConv(in, out, aggr='add', bias=True) as flexGCN builds it (modules.py:225, :239-246) on
+    batched dense x [B, N, F]:  out[b, v] = lin_rel( sum_{(u -> v)} x[b, u] ) + lin_root( x[b, v] ). The edge list is used
+    as given (directed, no self loops added, no edge weights). Parameters: `lin_rel.weight` [out, in], `lin_rel.bias`,
+    `lin_root.weight` (no bias). Restated from PyG's published semantics (PyG is not installable here: parity against
+    PyG itself is unpinned, as for gcn_conv)."""
+    src, dst = edge_index[0].long(), edge_index[1].long()
+    agg = torch.zeros_like(x).index_add_(-2, dst, x[..., src, :])
+    return (F.linear(agg, P[prefix + ".lin_rel.weight"], P[prefix + ".lin_rel.bias"])
+            + F.linear(x, P[prefix + ".lin_root.weight"]))
+
+
+def sage_conv(P, prefix: str, x: Tensor, edge_index: Tensor) -> Tensor:
+    """torch_geometric.nn.SAGEConv(in, out, aggr='mean', root_weight=True, bias=True, normalize=False, project=False):
+    out[b, v] = lin_l( mean_{(u -> v)} x[b, u] ) + lin_r( x[b, v] ); the mean over an empty neighbourhood is 0.
+    Parameters: `lin_l.weight`, `lin_l.bias`, `lin_r.weight` (no bias). Same pinning status as graph_conv."""
+    n = x.shape[-2]
+    src, dst = edge_index[0].long(), edge_index[1].long()
+    deg = torch.zeros(n, dtype=x.dtype).index_add_(0, dst, torch.ones(dst.numel(), dtype=x.dtype))
+    agg = torch.zeros_like(x).index_add_(-2, dst, x[..., src, :]) / deg.clamp_min(1.0)[:, None]
+    return F.linear(agg, P[prefix + ".lin_l.weight"], P[prefix + ".lin_l.bias"]) + F.linear(x, P[prefix + ".lin_r.weight"])
+
+
+CONVS = {"GCN": gcn_conv, "GC": graph_conv, "SAGE": sage_conv}
+
 ACTS = {"relu": torch.relu, "sigmoid": torch.sigmoid, "leakyrelu": lambda t: F.leaky_relu(t, 0.01),
         "tanh": torch.tanh, "gelu": F.gelu}
 
 
 def flexgcn(P, prefix: str, x: Tensor, edge_index: Tensor, num_convs: int, act: str, train: bool, noise: Noise,
-            p_drop: float = 0.2) -> Tensor:
-    """flexGCN.forward, modules.py:252-262 with conv='GCN'."""
+            p_drop: float = 0.2, conv: str = "GCN") -> Tensor:
+    """flexGCN.forward, modules.py:252-262 with conv in {'GCN', 'GC', 'SAGE'} (GAT is not restated)."""
     for k in range(num_convs):
-        x = gcn_conv(P, f"{prefix}.convs.{k}", x, edge_index)
+        x = CONVS[conv](P, f"{prefix}.convs.{k}", x, edge_index)
         x = batchnorm(P, f"{prefix}.bns.{k}", x.reshape(-1, x.shape[2]), train).view_as(x)
         x = ACTS[act](x)
         if train:
@@ -251,6 +276,7 @@ class Spec:
     node_embedding_dim: int = 0
     num_convs: int = 2
     activation: str = "relu"
+    conv: str = "GCN"                # flexGCN convolution: "GCN" | "GC" (GraphConv, the CLI default) | "SAGE"
     mmd_literal: bool = False        # evaluate the MMD kernels the reference's literal [x, y, dim] way (timing runs)
 
     def hidden(self, i: int) -> int:
@@ -323,10 +349,18 @@ def init_params(spec: Spec) -> Dict[str, Tensor]:
         fin = spec.input_dims[0]
         for k in range(spec.num_convs):
             # PyG GCNConv: lin = Linear(in, out, bias=False, weight_initializer='glorot'); bias = zeros(out)
-            w = torch.empty(emb, fin if k == 0 else emb)
-            torch.nn.init.xavier_uniform_(w)
-            P[f"encoders.0.convs.{k}.bias"] = torch.zeros(emb)
-            P[f"encoders.0.convs.{k}.lin.weight"] = w
+            cin = fin if k == 0 else emb
+            if spec.conv == "GCN":
+                w = torch.empty(emb, cin)
+                torch.nn.init.xavier_uniform_(w)
+                P[f"encoders.0.convs.{k}.bias"] = torch.zeros(emb)
+                P[f"encoders.0.convs.{k}.lin.weight"] = w
+            else:
+                # PyG GraphConv: lin_rel (bias) + lin_root (no bias); SAGEConv: lin_l (bias) + lin_r (no bias); PyG's
+                # Linear default init = kaiming_uniform(a = sqrt(5)) / uniform(+-1/sqrt(fan_in)), i.e. nn.Linear's
+                a, r = ("lin_rel", "lin_root") if spec.conv == "GC" else ("lin_l", "lin_r")
+                _linear(P, f"encoders.0.convs.{k}.{a}", cin, emb)
+                _linear(P, f"encoders.0.convs.{k}.{r}", cin, emb, bias=False)
             _bn(P, f"encoders.0.bns.{k}", emb)
         _linear(P, "encoders.0.fc", emb * spec.node_count, L)
     else:
@@ -409,7 +443,7 @@ def forward(P, spec: Spec, batch, train: bool, noise: Noise, edge_index: Optiona
         res["mean"], res["log_var"], res["x_hat"] = mean, log_var, x_hat
     elif spec.model == "GNN":
         x, y_dict = batch[0], batch[1]
-        emb = flexgcn(P, "encoders.0", x, edge_index, spec.num_convs, spec.activation, train, noise)
+        emb = flexgcn(P, "encoders.0", x, edge_index, spec.num_convs, spec.activation, train, noise, conv=spec.conv)
         outputs = _heads(P, spec, emb, train, noise)
         losses = _head_losses(spec, outputs, y_dict)
     else:

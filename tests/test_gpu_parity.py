@@ -61,7 +61,7 @@ def build_model(spec: Spec, batch, lr, P0=None, edge_index=None):
     if spec.model == "GNN":
         ds = _GDS(batch[0], batch[1], spec.variable_types, edge_index)
         model = fx.GNN(cfg, ds, targets, surv_event_var=spec.surv_event_var, surv_time_var=spec.surv_time_var,
-                       use_loss_weighting=spec.use_loss_weighting, device_type="gpu", gnn_conv_type="GCN")
+                       use_loss_weighting=spec.use_loss_weighting, device_type="gpu", gnn_conv_type=spec.conv)
         if P0 is not None:
             model.load_state_dict(P0, strict=True)
         return model.cuda()
@@ -336,6 +336,17 @@ GNN_CASES = {
     "ragged": (Spec(model="GNN", input_dims=[3], latent_dim=20, supervisor_hidden_dim=8, variables=["y", "c"],
                     variable_types=VT, num_classes={"c": 3}, node_count=77, node_embedding_dim=12, num_convs=3,
                     activation="relu"), 50, 120),
+    # GraphConv (the reference CLI's default convolution) and SAGEConv: neighbour sum / mean + root weight; graphs with
+    # isolated nodes, duplicate edges and self loops (synthetic_graph draws with replacement)
+    "graphconv": (Spec(model="GNN", input_dims=[1], latent_dim=32, supervisor_hidden_dim=16, variables=["y"],
+                       variable_types=VT, node_count=300, node_embedding_dim=32, num_convs=2, activation="relu",
+                       conv="GC"), 64, 2500),
+    "graphconv_ragged": (Spec(model="GNN", input_dims=[3], latent_dim=20, supervisor_hidden_dim=8, variables=["y", "c"],
+                              variable_types=VT, num_classes={"c": 3}, node_count=77, node_embedding_dim=12, num_convs=3,
+                              activation="tanh", conv="GC"), 50, 120),
+    "sage": (Spec(model="GNN", input_dims=[2], latent_dim=24, supervisor_hidden_dim=8, variables=["y"],
+                  variable_types=VT, node_count=150, node_embedding_dim=16, num_convs=2, activation="relu",
+                  conv="SAGE"), 40, 400),
 }
 
 

@@ -1,0 +1,66 @@
+"""CPU cross-check of the two independent torch formulations of the flexGCN convolutions: the oracle's restatement
+(oracle/restatement.py, what the GPU kernels are tested against) and the drop-in containers (flexynesis_b200/containers.py,
+what CPU-side inference of a saved model runs). torch_geometric is not installable here, so neither is pinned against PyG
+itself; they are pinned against each other and against a literal per-edge loop."""
+import pytest
+import torch
+
+from oracle.restatement import Spec, graph_conv, gcn_conv, init_params, sage_conv, synthetic_graph
+
+VT = {"y": "numerical"}
+
+
+def _graph(n, e, seed):
+    ei = synthetic_graph(n, e, seed)
+    extra = torch.tensor([[0, 1, 1, 5], [0, 2, 2, 5]])          # self loops on 0 and 5, a duplicated edge 1 -> 2
+    return torch.cat([ei, extra], 1)
+
+
+def _literal(kind, P, prefix, x, ei):
+    """per-edge python loop straight from the published definitions"""
+    B, N, F = x.shape
+    agg = torch.zeros_like(x)
+    deg = torch.zeros(N)
+    for s, d in ei.t().tolist():
+        agg[:, d] += x[:, s]
+        deg[d] += 1
+    if kind == "SAGE":
+        agg = agg / deg.clamp_min(1)[None, :, None]
+        a, r = "lin_l", "lin_r"
+    else:
+        a, r = "lin_rel", "lin_root"
+    return agg @ P[f"{prefix}.{a}.weight"].T + P[f"{prefix}.{a}.bias"] + x @ P[f"{prefix}.{r}.weight"].T
+
+
+@pytest.mark.parametrize("kind", ["GC", "SAGE"])
+def test_root_weight_convs_agree(kind):
+    from flexynesis_b200.containers import GraphConv, SAGEConv
+    torch.manual_seed(0)
+    spec = Spec(model="GNN", input_dims=[3], latent_dim=8, variables=["y"], variable_types=VT, node_count=40,
+                node_embedding_dim=12, num_convs=2, conv=kind)
+    P = init_params(spec)
+    ei = _graph(40, 90, 1)
+    x = torch.randn(5, 40, 3)
+    fn = graph_conv if kind == "GC" else sage_conv
+    want = fn(P, "encoders.0.convs.0", x, ei)
+    lit = _literal(kind, P, "encoders.0.convs.0", x, ei)
+    assert torch.allclose(want, lit, atol=1e-5)
+    mod = (GraphConv if kind == "GC" else SAGEConv)(3, 12)
+    mod.load_state_dict({k[len("encoders.0.convs.0."):]: v for k, v in P.items() if k.startswith("encoders.0.convs.0.")},
+                        strict=True)
+    assert torch.allclose(mod(x, ei), want, atol=1e-5)
+
+
+def test_state_dict_keys_follow_pyg():
+    from flexynesis_b200.containers import flexGCN
+    keys = {"GCN": {"convs.0.bias", "convs.0.lin.weight"},
+            "GC": {"convs.0.lin_rel.weight", "convs.0.lin_rel.bias", "convs.0.lin_root.weight"},
+            "SAGE": {"convs.0.lin_l.weight", "convs.0.lin_l.bias", "convs.0.lin_r.weight"}}
+    for conv, want in keys.items():
+        m = flexGCN(10, 2, 8, 4, num_convs=1, conv=conv)
+        got = {k for k in m.state_dict() if k.startswith("convs.")}
+        assert got == want, (conv, got)
+    with pytest.raises(ValueError):
+        flexGCN(10, 2, 8, 4, conv=None)
+    with pytest.raises(NotImplementedError):
+        flexGCN(10, 2, 8, 4, conv="GAT")
