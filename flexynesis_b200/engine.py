@@ -768,6 +768,55 @@ class TrunkEngine(EngineBase):
         B, Bp = ws["B"], ws["Bp"]
         return ws["F"][group * Bp:group * Bp + B, :self.latent]
 
+    # -- attribution: d out[var][:, cls] / d inputs in eval mode --
+    def _bn_eval_backward(self, bn: nn.BatchNorm1d, gname: str, bname: str, **kw):
+        """Backward of eval-mode BatchNorm (an affine map with the running statistics) + ReLU: the apply pass of
+        fxn_bn_act_bwd with zero reduction sums and (running_mean, rsqrt(running_var + eps)) as the saved statistics."""
+        a = self.arena
+        saved = torch.cat([bn.running_mean, torch.rsqrt(bn.running_var + EPS)]).contiguous()
+        zeros = torch.zeros(2 * bn.num_features, device=self.device)
+        L.bn_bwd(gamma=a.p(gname), beta=a.p(bname), saved=saved.data_ptr(), sums=zeros.data_ptr(), act=1, p_drop=0.0,
+                 pre_act=0, phase=2, **kw)
+
+    def input_gradients(self, x_list: Sequence[torch.Tensor], var: str, cls: int, weight: float, G: List[torch.Tensor]):
+        """G[i] [B x d_i] += weight * d(sum_b out[var][b, cls]) / d x_i, model in eval mode (running BatchNorm statistics,
+        no dropout): the forward pass, then the backward chain head -> fusion -> encoders with ONE extra dgrad GEMM per
+        modality (dX_i = dZ1_i W1_i) that training never needs. This is the integrand of captum's IntegratedGradients /
+        GradientShap as the reference calls them (direct_pred.py:432-590)."""
+        if self.G != 1:
+            raise NotImplementedError("attribution runs on the single-group trunk")
+        model, a = self.model, self.arena
+        ws = self.evaluate([list(x_list)], None, train_mode=False)
+        hw, hb = ws["heads"], self.heads
+        B, Lt, Lp = ws["B"], self.latent, self.Lp
+        i_v = hb.vars.index(var)
+        mlp = model.MLPs[var]
+        c0 = i_v * hb.shp
+        # d out[:, cls] / d Dh is row `cls` of layer_out.weight for every sample
+        hw["dDh"].zero_()
+        hw["dDh"][:, c0:c0 + hb.sh] = a.view(f"MLPs.{var}.layer_out.weight")[cls]
+        hw["dZh"].hi.zero_(); hw["dZh"].lo.zero_()
+        dz = hw["dZh"].cols_view(c0, hb.sh)
+        self._bn_eval_backward(mlp.batchnorm, f"MLPs.{var}.batchnorm.weight", f"MLPs.{var}.batchnorm.bias",
+                               V=fptr(hw["Zh"], c0), ldv=hw["Zh"].stride(0), dOut=fptr(hw["dDh"], c0),
+                               ldg=hw["dDh"].stride(0), rows=B, cols=hb.sh, dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+        L.gemm(B, Lt, hb.width, hw["dZh"], 0, hb.w1_planes(), 1, out=ws["dF_p"].rows_view(0, B))
+        for i in range(self.n):
+            enc = model.encoders[i]
+            h, hp = self.h[i], pad8(self.h[i])
+            dE = ws["dEcat_p"].cols_view(i * Lp, Lt)
+            if self.fused:
+                L.gemm(B, Lt, Lt, ws["dF_p"], 0, self.wf_planes(i), 1, out=dE)
+            L.gemm(B, h, Lt, dE, 0, self.wp(self.w2[i]), 1, C_ptr=ws["dD"][i].data_ptr(), ldc=hp)
+            dZ = ws["dZ"][i].rows_view(0, B)
+            self._bn_eval_backward(enc.batchnorm, f"encoders.{i}.batchnorm.weight", f"encoders.{i}.batchnorm.bias",
+                                   V=ws["Z"][i].data_ptr(), ldv=hp, dOut=ws["dD"][i].data_ptr(), ldg=hp, rows=B, cols=h,
+                                   dv_hi=dZ.hi_ptr, dv_lo=dZ.lo_ptr, ldp=dZ.ld)
+            # dX_i [B x d] = dZ1_i [B x h] * W1_i [h x d], accumulated into G[i] with the quadrature weight
+            L.gemm(B, self.d[i], h, dZ, 0, self.wp(self.w1[i]), 1, C_ptr=G[i].data_ptr(), ldc=G[i].stride(0),
+                   alpha=float(weight), accumulate=True)
+        return ws
+
 
 # ----------------------------------------------------------------------------------------------------
 # supervised_vae

@@ -524,3 +524,42 @@ def synthetic_graph(num_nodes: int, num_edges: int, seed: int = 0) -> Tensor:
     flip = rng.random(len(pairs)) < 0.5
     pairs[flip] = pairs[flip][:, ::-1]
     return torch.from_numpy(pairs.T.copy()).long()
+
+
+# ----------------------------------------------------------------------------------------------------
+# attribution (DirectPred.compute_feature_importance, direct_pred.py:432-590)
+# ----------------------------------------------------------------------------------------------------
+def attribution_path(method: str, n: int, generator=None):
+    """captum's path from the all-zero baseline to the input, restated from its published algorithm (captum is not
+    installable here, so this is unpinned against captum itself): IntegratedGradients(method='gausslegendre',
+    n_steps=n) evaluates the integrand at alphas = (1 + x_k) / 2 with step sizes w_k / 2, (x_k, w_k) the
+    Gauss-Legendre rule of order n; GradientShap with zero baselines and stdevs = 0 draws alphas ~ U(0, 1) and
+    averages."""
+    import numpy as np
+    if method == "IntegratedGradients":
+        x, w = np.polynomial.legendre.leggauss(int(n))
+        return list(0.5 * (1.0 + x)), list(0.5 * w)
+    a = torch.rand(int(n), generator=generator).tolist()
+    return a, [1.0 / n] * int(n)
+
+
+def feature_importance_sums(P, spec: Spec, dat: Dict[str, Tensor], var: str, alphas, weights) -> List[List[Tensor]]:
+    """[class][layer] -> sum over the batch of |x * sum_k w_k d out[var][:, class] / d x (alpha_k x)|, the quantity the
+    reference accumulates per batch (`a.abs().sum(dim=1)`, direct_pred.py:527, :553) before dividing by the number of
+    samples. Eval mode (running BatchNorm statistics, no dropout), torch autograd, DirectPred only."""
+    assert spec.model == "DirectPred"
+    xs = list(dat.values())
+    C = spec.head_out(var)
+    out = []
+    for cls in range(C):
+        G = [torch.zeros_like(x) for x in xs]
+        for al, w in zip(alphas, weights):
+            xk = [(x * float(al)).detach().requires_grad_(True) for x in xs]
+            Pc = {k: v.detach().clone() for k, v in P.items()}
+            emb = _fused_embedding(Pc, spec, xk, False, Noise())
+            o = _heads(Pc, spec, emb, False, Noise())[var]
+            o[:, cls].sum().backward()
+            for g, x in zip(G, xk):
+                g += float(w) * x.grad
+        out.append([(x * g).abs().sum(0) for x, g in zip(xs, G)])
+    return out

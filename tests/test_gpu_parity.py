@@ -430,3 +430,44 @@ def test_training_step_autograd_contract():
     opt = model.configure_optimizers()
     torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
     opt.step()   # torch optimizer on arena-backed parameters must work too
+
+
+def test_feature_importance_matches_oracle_attribution():
+    """compute_feature_importance: the engine's eval-mode input-gradient pass through head,
+    fusion and encoders, integrated along captum's Gauss-Legendre path, against torch autograd on the oracle."""
+    from oracle.restatement import attribution_path, feature_importance_sums, init_params
+    spec = Spec(model="DirectPred", input_dims=[300, 170], latent_dim=40, hidden_dim_factor=0.2, supervisor_hidden_dim=16,
+                variables=["y", "c"], variable_types=VT, num_classes={"c": 3})
+    torch.manual_seed(0)
+    P = init_params(spec)
+    for k in P:                                   # non-trivial running statistics and affine parameters
+        if k.endswith("running_mean"):
+            P[k] = torch.randn_like(P[k]) * 0.3
+        elif k.endswith("running_var"):
+            P[k] = torch.rand_like(P[k]) + 0.5
+        elif k.endswith("batchnorm.weight"):
+            P[k] = torch.rand_like(P[k]) + 0.5
+        elif k.endswith("batchnorm.bias"):
+            P[k] = torch.randn_like(P[k]) * 0.2
+    N = 700
+    dat, y = synthetic_batch(spec, N, 0)
+    model = build_model(spec, (dat, y, None), 1e-3, P)
+    ds = _DS(dat, y, spec.variable_types)
+    rep = Report()
+    for var, C in (("c", 3), ("y", 1)):
+        df = model.compute_feature_importance(ds, var, steps_or_samples=5, batch_size=256)
+        alphas, weights = attribution_path("IntegratedGradients", 5)
+        want = [[torch.zeros(d) for d in spec.input_dims] for _ in range(C)]
+        for s in range(0, N, 256):
+            part = feature_importance_sums(P, spec, {k: v[s:s + 256] for k, v in dat.items()}, var, alphas, weights)
+            for c in range(C):
+                for j in range(2):
+                    want[c][j] += part[c][j]
+        assert list(df.columns) == ["target_variable", "target_class", "target_class_label", "layer", "name", "importance"]
+        assert len(df) == C * sum(spec.input_dims)
+        for c in range(C):
+            for j, layer in enumerate(dat.keys()):
+                got = torch.tensor(df[(df.target_class == c) & (df.layer == layer)]["importance"].to_numpy())
+                rep.close(f"importance[{var}][class {c}][{layer}]", got, want[c][j] / N)
+        assert var in model.feature_importances
+    rep.finish()
