@@ -783,10 +783,10 @@ class TrunkEngine(EngineBase):
         no dropout): the forward pass, then the backward chain head -> fusion -> encoders with ONE extra dgrad GEMM per
         modality (dX_i = dZ1_i W1_i) that training never needs. This is the integrand of captum's IntegratedGradients /
         GradientShap as the reference calls them (direct_pred.py:432-590)."""
-        if self.G != 1:
-            raise NotImplementedError("attribution runs on the single-group trunk")
         model, a = self.model, self.arena
-        ws = self.evaluate([list(x_list)], None, train_mode=False)
+        # the triplet network attributes through its anchor branch: the three row groups get the same inputs and the
+        # backward chain below runs over the first B rows (group 0) only
+        ws = self.evaluate([list(x_list)] * self.G, None, train_mode=False)
         hw, hb = ws["heads"], self.heads
         B, Lt, Lp = ws["B"], self.latent, self.Lp
         i_v = hb.vars.index(var)
@@ -835,15 +835,18 @@ class VAEEngine(EngineBase):
     def __init__(self, model, device):
         super().__init__(model, device, extra_losses=(("mmd_loss", 3),))
         a, wp = self.arena, self.wplanes
-        self.n = len(model.encoders)
+        self.n = self.ne = len(model.encoders)
+        self.nd = len(model.decoders)           # CrossModalPred decodes into its own set of layers; supervised_vae: nd == ne
         self.d = [e.hidden_layers[0].in_features for e in model.encoders]
         self.h = [e.hidden_layers[0].out_features for e in model.encoders]
-        Lt, Lp, n = self.latent, self.Lp, self.n
+        self.dd = [m.FC_output.out_features for m in model.decoders]
+        self.hd = [m.hidden_layers[0].out_features for m in model.decoders]
+        Lt, Lp, n, nd = self.latent, self.Lp, self.ne, self.nd
         self.w1 = [wp.add_matrix(f"encoders.{i}.hidden_layers.0.weight") for i in range(n)]
         self.wm = [wp.add_matrix(f"encoders.{i}.FC_mean.weight") for i in range(n)]
         self.wv = [wp.add_matrix(f"encoders.{i}.FC_var.weight") for i in range(n)]
-        self.wd = [wp.add_matrix(f"decoders.{i}.hidden_layers.0.weight") for i in range(n)]
-        self.wo = [wp.add_matrix(f"decoders.{i}.FC_output.weight") for i in range(n)]
+        self.wd = [wp.add_matrix(f"decoders.{i}.hidden_layers.0.weight") for i in range(nd)]
+        self.wo = [wp.add_matrix(f"decoders.{i}.FC_output.weight") for i in range(nd)]
         # FC_mean / FC_log_var weights [L x n*L] as planes [L x n*Lp]: block i at columns [i*Lp, i*Lp + L)
         self.wfc_off = {}
         for name in ("FC_mean", "FC_log_var"):
@@ -851,8 +854,8 @@ class VAEEngine(EngineBase):
             for i in range(n):
                 wp.add_segment(f"{name}.weight", i * Lt, Lt, Lt, n * Lt, off + i * Lp, n * Lp)
             self.wfc_off[name] = off
-        self._finish_init(n)          # n - 1 modality streams + one for the heads / MMD chain
-        self.dims_dev = torch.tensor(self.d, dtype=torch.int32, device=self.device)
+        self._finish_init(max(n, nd))  # modality streams + one for the heads / MMD chain
+        self.dims_dev = torch.tensor(self.dd, dtype=torch.int32, device=self.device)
         self.mmd_slot = self.heads.loss_names.index("mmd_loss")
 
     def _aux_stream(self):
@@ -865,20 +868,20 @@ class VAEEngine(EngineBase):
     def workspace(self, B: int) -> dict:
         if B in self.ws:
             return self.ws[B]
-        dev, n, Lt, Lp, P = self.device, self.n, self.latent, self.Lp, self.PRIOR
+        dev, n, nd, Lt, Lp, P = self.device, self.ne, self.nd, self.latent, self.Lp, self.PRIOR
         mt = L.stat_tiles(B)
         f = lambda *shape: torch.zeros(*shape, device=dev)
         ws = dict(B=B)
         ws["X"] = [Planes.empty(B, self.d[i], dev) for i in range(n)]
-        ws["x_f32"] = [None] * n
-        for tag in ("", "d"):     # encoder / decoder hidden blocks
-            ws["A" + tag] = [f(B, pad8(self.h[i])) for i in range(n)]
-            ws["Y" + tag] = [Planes.empty(B, self.h[i], dev) for i in range(n)]
-            ws["partials" + tag] = [f(mt * 2 * self.h[i]) for i in range(n)]
-            ws["saved" + tag] = [f(2 * self.h[i]) for i in range(n)]
-            ws["sums" + tag] = [f(2 * self.h[i]) for i in range(n)]
-            ws["dY" + tag] = [f(B, pad8(self.h[i])) for i in range(n)]
-            ws["dZ" + tag] = [Planes.empty(B, self.h[i], dev) for i in range(n)]
+        ws["x_f32"] = [None] * nd                 # reconstruction targets (fp32), one per decoder
+        for tag, cnt, hh in (("", n, self.h), ("d", nd, self.hd)):     # encoder / decoder hidden blocks
+            ws["A" + tag] = [f(B, pad8(hh[i])) for i in range(cnt)]
+            ws["Y" + tag] = [Planes.empty(B, hh[i], dev) for i in range(cnt)]
+            ws["partials" + tag] = [f(mt * 2 * hh[i]) for i in range(cnt)]
+            ws["saved" + tag] = [f(2 * hh[i]) for i in range(cnt)]
+            ws["sums" + tag] = [f(2 * hh[i]) for i in range(cnt)]
+            ws["dY" + tag] = [f(B, pad8(hh[i])) for i in range(cnt)]
+            ws["dZ" + tag] = [Planes.empty(B, hh[i], dev) for i in range(cnt)]
         ws["Mcat_p"] = Planes.empty(B, n * Lp, dev, ld=n * Lp)
         ws["Vcat_p"] = Planes.empty(B, n * Lp, dev, ld=n * Lp)
         for k in ("mean", "s", "eps", "z", "dz", "KZ"):
@@ -888,33 +891,39 @@ class VAEEngine(EngineBase):
         ws["ds_p"] = Planes.empty(B, Lt, dev, ld=Lp)
         ws["dM_p"] = [Planes.empty(B, Lt, dev, ld=Lp) for _ in range(n)]
         ws["dV_p"] = [Planes.empty(B, Lt, dev, ld=Lp) for _ in range(n)]
-        ws["G"] = [Planes.empty(B, self.d[i], dev) for i in range(n)]
-        ws["xhat"] = [None] * n
-        ws["mse_acc"] = f(n)
+        ws["G"] = [Planes.empty(B, self.dd[i], dev) for i in range(nd)]
+        ws["xhat"] = [None] * nd
+        ws["mse_acc"] = f(nd)
         ws["wts"] = f(max(self.heads.n_losses, 1))
-        # MMD
-        ws["T"] = [f(P, Lp) for _ in range(n)]
-        ws["T_p"] = [Planes.empty(P, Lt, dev, ld=Lp) for _ in range(n)]
-        ws["rz"], ws["rt"] = f(B), [f(P) for _ in range(n)]
+        # MMD (one prior draw and one K(t, z) per decoded layer, as MMD_loss is called once per output layer)
+        ws["T"] = [f(P, Lp) for _ in range(nd)]
+        ws["T_p"] = [Planes.empty(P, Lt, dev, ld=Lp) for _ in range(nd)]
+        ws["rz"], ws["rt"] = f(B), [f(P) for _ in range(nd)]
         ws["Kzz_p"] = Planes.empty(B, B, dev)
-        ws["Ktz_p"] = [Planes.empty(P, B, dev) for _ in range(n)]
+        ws["Ktz_p"] = [Planes.empty(P, B, dev) for _ in range(nd)]
         ws["Ktt_p"] = Planes.empty(P, P, dev)
-        ws["cs_zz"], ws["cs_tz"], ws["cs_tt"] = f(B), f(n, B), f(n, P)
-        ws["KT"] = f(n, B, Lp)
+        ws["cs_zz"], ws["cs_tz"], ws["cs_tt"] = f(B), f(nd, B), f(nd, P)
+        ws["KT"] = f(nd, B, Lp)
         ws["heads"] = self.heads.workspace(B)
         self.ws[B] = ws
         return ws
 
-    def stage_inputs(self, ws, x_list: Sequence[torch.Tensor]):
+    def stage_inputs(self, ws, x_list: Sequence[torch.Tensor], targets: Optional[Sequence[torch.Tensor]] = None):
+        """x_list: one matrix per encoder; targets: one per decoder (default: the inputs themselves, supervised_vae)."""
         for i, x in enumerate(x_list):
             x = self._input(x)
-            ws["x_f32"][i] = x                      # the reconstruction error reads the fp32 input
             self.inputs.get((ws["B"], i), x, ws["X"][i])
+            if targets is None:
+                ws["x_f32"][i] = x                  # the reconstruction error reads the fp32 input
+        if targets is not None:
+            for i, t in enumerate(targets):
+                ws["x_f32"][i] = self._input(t).contiguous()
 
     def _hidden_fwd(self, ws, tag: str, i: int, prefix: str, inp: Planes, K: int, wplanes: Planes, train: bool):
         """Linear -> LeakyReLU(0.2) (GEMM epilogue) -> BatchNorm1d; returns nothing, fills A/Y/saved."""
         a = self.arena
-        B, h, hp = ws["B"], self.h[i], pad8(self.h[i])
+        hh = self.hd if tag == "d" else self.h
+        B, h, hp = ws["B"], hh[i], pad8(hh[i])
         A, Y = ws["A" + tag][i], ws["Y" + tag][i]
         bn = self.model.get_submodule(prefix).hidden_layers[2]
         L.gemm(B, h, K, inp, 0, wplanes, 0, C_ptr=A.data_ptr(), ldc=hp, bias=a.p(f"{prefix}.hidden_layers.0.bias"),
@@ -928,7 +937,8 @@ class VAEEngine(EngineBase):
     def _hidden_bwd(self, ws, tag: str, i: int, prefix: str):
         """BatchNorm backward + LeakyReLU derivative: dY (fp32) -> dZ planes; fills d gamma / beta / bias."""
         a = self.arena
-        B, h, hp = ws["B"], self.h[i], pad8(self.h[i])
+        hh = self.hd if tag == "d" else self.h
+        B, h, hp = ws["B"], hh[i], pad8(hh[i])
         dz = ws["dZ" + tag][i]
         self.bn_backward(V=ws["A" + tag][i].data_ptr(), ldv=hp, dOut=ws["dY" + tag][i].data_ptr(), ldg=hp, rows=B, cols=h,
                          gamma=a.p(f"{prefix}.hidden_layers.2.weight"), beta=a.p(f"{prefix}.hidden_layers.2.bias"),
@@ -940,7 +950,7 @@ class VAEEngine(EngineBase):
     # ---- forward: encoders -> latent -> decoders | heads | MMD ----
     def _forward(self, ws, y, train: bool, noise, with_loss: bool, want_xhat: bool = False):
         a, hw = self.arena, ws["heads"]
-        B, n, Lt, Lp, P = ws["B"], self.n, self.latent, self.Lp, self.PRIOR
+        B, n, nd, Lt, Lp, P = ws["B"], self.ne, self.nd, self.latent, self.Lp, self.PRIOR
         noise = noise or {}
         hw["acc"].zero_()
         ws["mse_acc"].zero_()
@@ -969,15 +979,15 @@ class VAEEngine(EngineBase):
                       ws["z_p"])
         # decoders, and beside them (aux stream) the heads and the MMD chain
         self._fork()
-        for i in range(n):
+        for i in range(nd):
             with torch.cuda.stream(self._stream_for(i)):
                 self._hidden_fwd(ws, "d", i, f"decoders.{i}", ws["z_p"], Lt, self.wp(self.wd[i]), train)
                 x = ws["x_f32"][i]
                 if want_xhat and ws["xhat"][i] is None:
-                    ws["xhat"][i] = torch.zeros(B, self.d[i], device=self.device)
-                scale = 2.0 / (float(B) * self.d[i] * n)
-                L.gemm(B, self.d[i], self.h[i], ws["Yd"][i], 0, self.wp(self.wo[i]), 0,
-                       C_ptr=ws["xhat"][i].data_ptr() if want_xhat else None, ldc=self.d[i],
+                    ws["xhat"][i] = torch.zeros(B, self.dd[i], device=self.device)
+                scale = 2.0 / (float(B) * self.dd[i] * nd)
+                L.gemm(B, self.dd[i], self.hd[i], ws["Yd"][i], 0, self.wp(self.wo[i]), 0,
+                       C_ptr=ws["xhat"][i].data_ptr() if want_xhat else None, ldc=self.dd[i],
                        bias=a.p(f"decoders.{i}.FC_output.bias"), epi_act=3, out=ws["G"][i],
                        mse_x=x.data_ptr(), ldx=x.stride(0), mse_acc=fptr(ws["mse_acc"], i),
                        colstats=a.g(f"decoders.{i}.FC_output.bias") if train else None, stats_mode=3,
@@ -987,12 +997,12 @@ class VAEEngine(EngineBase):
         self._join()
         if with_loss:
             L.mmd_finish(ws["cs_zz"].data_ptr(), ws["cs_tt"].data_ptr(), ws["cs_tz"].data_ptr(),
-                         ws["mse_acc"].data_ptr(), self.dims_dev.data_ptr(), n, B, P, fptr(hw["acc"], 2 * self.mmd_slot))
+                         ws["mse_acc"].data_ptr(), self.dims_dev.data_ptr(), nd, B, P, fptr(hw["acc"], 2 * self.mmd_slot))
             hb.total(hw)
 
     def _heads_and_mmd(self, ws, y, train, noise, with_loss):
         a, hw, hb = self.arena, ws["heads"], self.heads
-        B, n, Lt, Lp, P = ws["B"], self.n, self.latent, self.Lp, self.PRIOR
+        B, n, Lt, Lp, P = ws["B"], self.nd, self.latent, self.Lp, self.PRIOR      # n: decoded layers
         hb.forward(hw, ws["z_p"], B, y, train, noise, with_loss=with_loss)
         if with_loss:
             # MMD: Gaussian-kernel Gram matrices + column sums
@@ -1017,23 +1027,24 @@ class VAEEngine(EngineBase):
 
     def forward_backward(self, x_groups, y, masks=None):
         x_list = x_groups[0]
+        targets = x_groups[1] if len(x_groups) > 1 else None       # CrossModalPred: the layers to reconstruct
         B = x_list[0].shape[0]
         ws = self.workspace(B)
         hw, a = ws["heads"], self.arena
-        n, Lt, Lp, P = self.n, self.latent, self.Lp, self.PRIOR
+        n, nd, Lt, Lp, P = self.ne, self.nd, self.latent, self.Lp, self.PRIOR
         y = self._labels(y)
         self.ensure_fresh()
-        self.stage_inputs(ws, x_list)
+        self.stage_inputs(ws, x_list, targets)
         self._forward(ws, y, True, masks, True)
         w_mmd = fptr(ws["wts"], self.mmd_slot)
         # ---- backward ----
         if not self.heads.backward(hw, ws["z_p"], B, y, masks, None, ws["dz"], None):
             ws["dz"].zero_()
         self._fork()
-        for i in range(n):
+        for i in range(nd):
             with torch.cuda.stream(self._stream_for(i)):
-                scale = 2.0 / (float(B) * self.d[i] * n)
-                h, hp, d = self.h[i], pad8(self.h[i]), self.d[i]
+                scale = 2.0 / (float(B) * self.dd[i] * nd)
+                h, hp, d = self.hd[i], pad8(self.hd[i]), self.dd[i]
                 # dYd = c * G * Wo ; dWo = c * G^T * Yd         (c = 2 / (B d n) * weight of mmd_loss)
                 L.gemm(B, h, d, ws["G"][i], 0, self.wp(self.wo[i]), 1, C_ptr=ws["dYd"][i].data_ptr(), ldc=hp,
                        alpha=scale, alpha_dev=w_mmd)
@@ -1044,14 +1055,14 @@ class VAEEngine(EngineBase):
                        ldc=Lt, splitk=-1)
         with torch.cuda.stream(self._aux_stream()):      # MMD gradient operands beside the decoder chains
             L.gemm(B, Lt, B, ws["Kzz_p"], 0, ws["z_p"], 1, C_ptr=ws["KZ"].data_ptr(), ldc=Lp)
-            for i in range(n):
+            for i in range(nd):
                 L.gemm(B, Lt, P, ws["Ktz_p"][i], 1, ws["T_p"][i], 1, C_ptr=ws["KT"][i].data_ptr(), ldc=Lp)
         self._join()
-        for i in range(n):
-            L.gemm(B, Lt, self.h[i], ws["dZd"][i], 0, self.wp(self.wd[i]), 1, C_ptr=ws["dz"].data_ptr(), ldc=Lp,
+        for i in range(nd):
+            L.gemm(B, Lt, self.hd[i], ws["dZd"][i], 0, self.wp(self.wd[i]), 1, C_ptr=ws["dz"].data_ptr(), ldc=Lp,
                    accumulate=True)
         L.mmd_grad(ws["z"].data_ptr(), Lp, ws["cs_zz"].data_ptr(), ws["KZ"].data_ptr(), ws["cs_tz"].data_ptr(),
-                   ws["KT"].data_ptr(), Lp, n, B, Lt, P, w_mmd, ws["dz"].data_ptr(), Lp)
+                   ws["KT"].data_ptr(), Lp, nd, B, Lt, P, w_mmd, ws["dz"].data_ptr(), Lp)
         L.reparam_bwd(ws["dz"].data_ptr(), ws["eps"].data_ptr(), Lp, B, Lt, ws["dm_p"], ws["ds_p"],
                       a.g("FC_mean.bias"), a.g("FC_log_var.bias"))
         self._fork()
@@ -1081,9 +1092,10 @@ class VAEEngine(EngineBase):
 
     def evaluate(self, x_groups, y=None, train_mode: bool = False, masks=None, want_xhat: bool = False):
         x_list = x_groups[0]
+        targets = x_groups[1] if len(x_groups) > 1 else None
         ws = self.workspace(x_list[0].shape[0])
         self.ensure_fresh()
-        self.stage_inputs(ws, x_list)
+        self.stage_inputs(ws, x_list, targets)
         yl = self._labels(y) if y is not None else None
         self._forward(ws, yl, train_mode, masks, y is not None, want_xhat)
         return ws

@@ -552,6 +552,89 @@ class supervised_vae(_EngineModel):
         return torch.cat(outs, dim=0)
 
 
+class CrossModalPred(supervised_vae):
+    """Cross-modality VAE (flexynesis/models/crossmodal_pred.py:31-187): Encoders over `input_layers`, Decoders into
+    `output_layers` (each defaulting to every layer of the dataset), the same MMD + reconstruction + supervisor-head
+    objective as supervised_vae (:293-351) with the reconstruction targets taken from the OUTPUT layers. Runs on the
+    VAE engine, which keeps separate encoder / decoder layer sets."""
+
+    def __init__(self, config, dataset, target_variables=None, batch_variables=None, surv_event_var=None,
+                 surv_time_var=None, input_layers=None, output_layers=None, use_loss_weighting=True, device_type=None):
+        _EngineModel.__init__(self)
+        self.config = config
+        self.target_variables = list(target_variables or [])
+        self.surv_event_var, self.surv_time_var = surv_event_var, surv_time_var
+        if surv_event_var is not None and surv_time_var is not None:
+            self.target_variables = self.target_variables + [surv_event_var]
+        self.batch_variables = batch_variables
+        self.variables = self.target_variables + batch_variables if batch_variables else self.target_variables
+        self.variable_types = dataset.variable_types
+        self.ann = dataset.ann
+        self.input_layers = list(input_layers) if input_layers else list(dataset.dat.keys())
+        self.output_layers = list(output_layers) if output_layers else list(dataset.dat.keys())
+        self.layers = self.input_layers
+        self.feature_importances = {}
+        self.nan_detected = False
+        self.device_type = device_type
+        self.use_loss_weighting = use_loss_weighting
+        if use_loss_weighting:
+            self.log_vars = nn.ParameterDict(
+                {v: nn.Parameter(torch.zeros(1)) for v in itertools.chain(self.variables, ["mmd_loss"])})
+        latent, f = config["latent_dim"], config["hidden_dim_factor"]
+        self.input_dims = [len(dataset.features[k]) for k in self.input_layers]
+        self.output_dims = [len(dataset.features[k]) for k in self.output_layers]
+        self.encoders = nn.ModuleList([Encoder(d, [int(d * f)], latent) for d in self.input_dims])
+        self.FC_mean = nn.Linear(len(self.input_layers) * latent, latent)
+        self.FC_log_var = nn.Linear(len(self.input_layers) * latent, latent)
+        self.decoders = nn.ModuleList([Decoder(latent, [int(d * f)], d) for d in self.output_dims])
+        self.MLPs = nn.ModuleDict()
+        for var in self.variables:
+            classes = 1 if self.variable_types[var] == "numerical" else len(np.unique(self.ann[var]))
+            self.MLPs[var] = MLP(latent, config["supervisor_hidden_dim"], classes)
+
+    def _split_batch(self, batch):
+        dat, y_dict = batch[0], batch[1]
+        return [[dat[k] for k in self.input_layers], [dat[k] for k in self.output_layers]], y_dict
+
+    def _batches(self, dataset, batch_size):
+        n = len(dataset)
+        for s in range(0, n, batch_size):
+            yield [dataset.dat[k][s:s + batch_size] for k in self.input_layers], list(dataset.samples[s:s + batch_size])
+
+    def forward(self, x_list_input):
+        x_list = list(x_list_input)
+        use_engine = all(x.is_cuda and not x.requires_grad for x in x_list) and not (
+            self.training and torch.is_grad_enabled())
+        if use_engine:
+            eng = self.engine(x_list[0].device)
+            B = x_list[0].shape[0]
+            # the fused decoder epilogue always reads a reconstruction target; inference has none: zeros
+            dummy = [torch.zeros(B, d, device=x_list[0].device) for d in self.output_dims]
+            ws = eng.evaluate([x_list, dummy], None, train_mode=self.training, want_xhat=True)
+            Lt = eng.latent
+            return ([t.clone() for t in ws["xhat"]], ws["z"][:, :Lt].clone(), ws["mean"][:, :Lt].clone(),
+                    ws["s"][:, :Lt].clone(), self._outputs_from_ws(eng, ws))
+        mean, log_var = self.multi_encoder(x_list)
+        z = self.reparameterization(mean, log_var)
+        return [dec(z) for dec in self.decoders], z, mean, log_var, {v: mlp(z) for v, mlp in self.MLPs.items()}
+
+    def decode(self, dataset):
+        """{output layer: DataFrame [samples x features]} of reconstructions (crossmodal_pred.py:467-481)."""
+        self.eval()
+        device = _resolve_device(self.device_type)
+        self.to(device)
+        outs, names = [[] for _ in self.output_layers], []
+        with torch.no_grad():
+            for xs, samples in self._batches(dataset, 4096 if device.type == "cuda" else 64):
+                x_hat = self.forward([x.to(device, torch.float32) for x in xs])[0]
+                for j, t in enumerate(x_hat):
+                    outs[j].append(t.detach().cpu())
+                names.extend(samples)
+        # features x samples, as the reference lays the frames out
+        return {k: pd.DataFrame(torch.cat(outs[j], 0).numpy().T, index=dataset.features[k], columns=names)
+                for j, k in enumerate(self.output_layers)}
+
+
 class GNN(_EngineModel):
     """Graph-convolutional early-fusion model (flexynesis/models/gnn_early.py:55-140): one flexGCN over node features
     [B, N, F] with a graph shared by all samples, supervisor heads on its embedding."""

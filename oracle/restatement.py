@@ -276,6 +276,9 @@ class Spec:
     node_embedding_dim: int = 0
     num_convs: int = 2
     activation: str = "relu"
+    # CrossModalPred only: indices (into input_dims / the batch's layers) of the encoded and of the reconstructed layers
+    in_idx: Optional[List[int]] = None
+    out_idx: Optional[List[int]] = None
     conv: str = "GCN"                # flexGCN convolution: "GCN" | "GC" (GraphConv, the CLI default) | "SAGE"
     mmd_literal: bool = False        # evaluate the MMD kernels the reference's literal [x, y, dim] way (timing runs)
 
@@ -287,7 +290,8 @@ class Spec:
         return 1 if self.variable_types[var] == "numerical" else self.num_classes[var]
 
     def loss_names(self) -> List[str]:
-        extra = {"supervised_vae": ["mmd_loss"], "MultiTripletNetwork": ["triplet_loss"]}.get(self.model, [])
+        extra = {"supervised_vae": ["mmd_loss"], "CrossModalPred": ["mmd_loss"],
+                 "MultiTripletNetwork": ["triplet_loss"]}.get(self.model, [])
         return list(self.variables) + extra
 
 
@@ -341,6 +345,26 @@ def init_params(spec: Spec) -> Dict[str, Tensor]:
         _linear(P, "FC_log_var", n * L, L)
         for i, d in enumerate(spec.input_dims):
             h = spec.hidden(i)
+            _linear(P, f"decoders.{i}.hidden_layers.0", L, h, xavier=True)
+            _bn(P, f"decoders.{i}.hidden_layers.2", h)
+            _linear(P, f"decoders.{i}.FC_output", h, d, xavier=True)
+    elif spec.model == "CrossModalPred":
+        # crossmodal_pred.py:80-121: Encoders over the input layers, FC_mean / FC_log_var, Decoders into the output
+        # layers; hidden width int(d * factor) (no clamp)
+        ins = spec.in_idx if spec.in_idx is not None else list(range(len(spec.input_dims)))
+        outs = spec.out_idx if spec.out_idx is not None else list(range(len(spec.input_dims)))
+        for i, li in enumerate(ins):
+            d = spec.input_dims[li]
+            h = int(d * spec.hidden_dim_factor)
+            _linear(P, f"encoders.{i}.hidden_layers.0", d, h, xavier=True)
+            _bn(P, f"encoders.{i}.hidden_layers.2", h)
+            _linear(P, f"encoders.{i}.FC_mean", h, L, xavier=True)
+            _linear(P, f"encoders.{i}.FC_var", h, L, xavier=True)
+        _linear(P, "FC_mean", len(ins) * L, L)
+        _linear(P, "FC_log_var", len(ins) * L, L)
+        for i, li in enumerate(outs):
+            d = spec.input_dims[li]
+            h = int(d * spec.hidden_dim_factor)
             _linear(P, f"decoders.{i}.hidden_layers.0", L, h, xavier=True)
             _bn(P, f"decoders.{i}.hidden_layers.2", h)
             _linear(P, f"decoders.{i}.FC_output", h, d, xavier=True)
@@ -435,6 +459,26 @@ def forward(P, spec: Spec, batch, train: bool, noise: Noise, edge_index: Optiona
         outputs = _heads(P, spec, z, train, noise)
         per_layer = []
         for i, x in enumerate(x_list):                                           # MMD_loss, :532-550
+            prior = noise.normal(f"mmd_prior.{i}", (200, z.shape[1]), z)
+            per_layer.append(mmd(prior, z, literal=spec.mmd_literal) + (x_hat[i] - x).pow(2).mean())
+        losses = {"mmd_loss": torch.mean(torch.stack(per_layer))}
+        losses.update(_head_losses(spec, outputs, y_dict))
+        emb = z
+        res["mean"], res["log_var"], res["x_hat"] = mean, log_var, x_hat
+    elif spec.model == "CrossModalPred":
+        dat, y_dict = batch[0], batch[1]
+        layers = list(dat.values())
+        ins = spec.in_idx if spec.in_idx is not None else list(range(len(layers)))
+        outs = spec.out_idx if spec.out_idx is not None else list(range(len(layers)))
+        x_in, x_out = [layers[i] for i in ins], [layers[i] for i in outs]
+        means, logvars = zip(*[vae_encoder(P, f"encoders.{i}", x, train) for i, x in enumerate(x_in)])
+        mean = F.linear(torch.cat(means, 1), P["FC_mean.weight"], P["FC_mean.bias"])
+        log_var = F.linear(torch.cat(logvars, 1), P["FC_log_var.weight"], P["FC_log_var.bias"])
+        z = mean + log_var * noise.normal("epsilon", log_var.shape, log_var)     # crossmodal_pred.py:189-202
+        x_hat = [vae_decoder(P, f"decoders.{i}", z, train) for i in range(len(x_out))]
+        outputs = _heads(P, spec, z, train, noise)
+        per_layer = []
+        for i, x in enumerate(x_out):                                            # :321-328, MMD_loss per OUTPUT layer
             prior = noise.normal(f"mmd_prior.{i}", (200, z.shape[1]), z)
             per_layer.append(mmd(prior, z, literal=spec.mmd_literal) + (x_hat[i] - x).pow(2).mean())
         losses = {"mmd_loss": torch.mean(torch.stack(per_layer))}

@@ -71,8 +71,13 @@ def build_model(spec: Spec, batch, lr, P0=None, edge_index=None):
     else:
         ds = _DS(batch[0], batch[1], spec.variable_types)
         cls = getattr(fx, spec.model)
+    extra = {}
+    if spec.model == "CrossModalPred":
+        keys = list(batch[0].keys())
+        extra = dict(input_layers=[keys[i] for i in spec.in_idx] if spec.in_idx is not None else None,
+                     output_layers=[keys[i] for i in spec.out_idx] if spec.out_idx is not None else None)
     model = cls(cfg, ds, targets, surv_event_var=spec.surv_event_var, surv_time_var=spec.surv_time_var,
-                use_loss_weighting=spec.use_loss_weighting, device_type="gpu")
+                use_loss_weighting=spec.use_loss_weighting, device_type="gpu", **extra)
     if P0 is not None:
         model.load_state_dict(P0, strict=True)
     return model.cuda()
@@ -144,13 +149,18 @@ def gate_margin_units(spec, P, batch, res, masks, margin=2e-4):
             for d in batch[:3]:
                 for i, x in enumerate(d.values()):
                     block(f"encoders.{i}", x)
+        elif spec.model == "CrossModalPred":
+            layers = list(batch[0].values())
+            for i, li in enumerate(spec.in_idx if spec.in_idx is not None else range(len(layers))):
+                block(f"encoders.{i}", layers[li])
         elif spec.model != "GNN":
             for i, x in enumerate(batch[0].values()):
                 block(f"encoders.{i}", x)
         for v in spec.variables:
             block(f"MLPs.{v}", res["embedding"].detach())
-        if spec.model == "supervised_vae":
-            for i in range(len(spec.input_dims)):
+        if spec.model in ("supervised_vae", "CrossModalPred"):
+            nd = len(spec.out_idx) if (spec.model == "CrossModalPred" and spec.out_idx is not None) else len(spec.input_dims)
+            for i in range(nd):
                 block(f"decoders.{i}", res["embedding"].detach())
     return out
 
@@ -178,7 +188,7 @@ def compare_step(rep, model, spec, batch, cb, st, s, P_before_cpu, lr):
     ws = eng.forward_backward(groups, y, masks)
     for k, v in st["outputs"].items():
         rep.close(f"step{s} outputs[{k}]", ws["heads"]["logits"][k], v)
-    if st.get("embedding") is not None and spec.model == "supervised_vae":
+    if st.get("embedding") is not None and spec.model in ("supervised_vae", "CrossModalPred"):
         rep.close(f"step{s} z", eng.embedding(ws), st["embedding"])
     vals = eng.losses(ws)
     for k, v in st["losses"].items():
@@ -289,6 +299,13 @@ CASES = {
     # latent 128 as in config 3, classification + regression heads, one modality, batch = 512
     "svae_heads": (Spec(model="supervised_vae", input_dims=[400], latent_dim=128, hidden_dim_factor=0.2,
                         supervisor_hidden_dim=32, variables=["y", "c"], variable_types=VT, num_classes={"c": 4}), 512),
+    # CrossModalPred: encode layers 0 and 2, reconstruct layers 1 and 2 (one layer only decoded, one in both sets)
+    "crossmodal": (Spec(model="CrossModalPred", input_dims=[300, 220, 150], latent_dim=32, hidden_dim_factor=0.15,
+                        supervisor_hidden_dim=16, variables=["y", "e"], variable_types=VT, surv_event_var="e",
+                        surv_time_var="t", in_idx=[0, 2], out_idx=[1, 2]), 260),
+    # defaults: every layer encoded and reconstructed (then it coincides with supervised_vae up to the hidden clamp)
+    "crossmodal_all": (Spec(model="CrossModalPred", input_dims=[200, 90], latent_dim=24, hidden_dim_factor=0.2,
+                            supervisor_hidden_dim=8, variables=["c"], variable_types=VT, num_classes={"c": 3}), 200),
 }
 
 
