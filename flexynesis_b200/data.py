@@ -99,3 +99,81 @@ class DeviceBatcher:
                 out._fxn_tag = self._tag   # written through a raw pointer: tell the engine's plane cache it changed
                 dat[k] = out
             yield dat, {k: v[idx] for k, v in self.ann.items()}, None
+
+
+class DeviceTripletBatcher:
+    """(anchor, positive, negative, y_dict) batches for MultiTripletNetwork built ON THE DEVICE: replaces
+    TripletMultiOmicDataset.__getitem__ + default_collate (flexynesis/data.py:1088-1151), which draw one positive and
+    one negative per anchor with numpy / random on the host and stack 3 x B dict lookups per batch.
+
+    Same sampling law as the reference: anchors are the samples whose `main_var` label is not NaN (each once per epoch,
+    shuffled); the positive is uniform over the OTHER samples with the anchor's label; the negative label is uniform
+    over the other label groups -- missing labels form one group "NA" that negatives may come from (:1122-1127) -- and
+    the negative uniform inside it. (A label with a single sample makes the reference spin forever; here the anchor is
+    its own positive.) Index arithmetic is a handful of torch ops on [B]-vectors; the rows are gathered by
+    fxn_gather_rows from the HBM-resident matrices into three persistent buffers per layer."""
+
+    def __init__(self, dataset, main_var: str, batch_size: int, device, shuffle: bool = True, drop_last: bool = True,
+                 seed: int = 0):
+        base = getattr(dataset, "dataset", dataset)
+        self.device = torch.device(device)
+        self.dat = {k: torch.as_tensor(v).to(self.device, torch.float32).contiguous() for k, v in base.dat.items()}
+        self.ann = {k: torch.as_tensor(v).to(self.device, torch.float32).contiguous() for k, v in base.ann.items()}
+        self.main_var, self.batch_size, self.shuffle, self.drop_last = main_var, batch_size, shuffle, drop_last
+        lab = torch.as_tensor(base.ann[main_var]).to(torch.float64).cpu()
+        nan = torch.isnan(lab)
+        uniq = torch.unique(lab[~nan])
+        gid = torch.searchsorted(uniq, torch.nan_to_num(lab, nan=float(uniq[0]) if uniq.numel() else 0.0))
+        gid[nan] = uniq.numel()                                   # the "NA" group
+        self.n_groups = int(uniq.numel()) + int(bool(nan.any()))
+        if self.n_groups < 2:
+            raise ValueError("triplet sampling needs at least two label groups")
+        order = torch.sort(gid, stable=True).indices
+        count = torch.bincount(gid, minlength=self.n_groups)
+        start = torch.cumsum(count, 0) - count
+        rank = torch.empty_like(order)
+        rank[order] = torch.arange(order.numel()) - start[gid[order]]
+        dev = self.device
+        self.gid, self.order, self.count, self.start, self.rank = (t.to(dev) for t in (gid, order, count, start, rank))
+        self.valid = torch.nonzero(~nan).flatten().to(dev)
+        self.gen = torch.Generator(device=dev).manual_seed(seed)
+        self._buf = [{k: torch.empty(batch_size, v.shape[1], device=dev) for k, v in self.dat.items()} for _ in range(3)]
+        self._tag = 0
+
+    def __len__(self):
+        n = self.valid.numel()
+        return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
+
+    def sample_indices(self, anchors: torch.Tensor):
+        """positive / negative sample indices for a vector of anchor indices (device tensors)."""
+        g = self.gid[anchors]
+        cnt = self.count[g]
+        u = torch.rand(anchors.numel(), 3, device=self.device, generator=self.gen, dtype=torch.float64)
+        r = torch.minimum((u[:, 0] * (cnt - 1).clamp_min(1)).long(), (cnt - 2).clamp_min(0))
+        r = r + (r >= self.rank[anchors]).long()                  # skip the anchor's own slot
+        pos = torch.where(cnt > 1, self.order[self.start[g] + r.clamp_max(cnt - 1)], anchors)
+        gn = torch.minimum((u[:, 1] * (self.n_groups - 1)).long(), torch.full_like(g, self.n_groups - 2))
+        gn = gn + (gn >= g).long()                                # uniform over the OTHER groups
+        cn = self.count[gn]
+        neg = self.order[self.start[gn] + torch.minimum((u[:, 2] * cn).long(), cn - 1)]
+        return pos, neg
+
+    def _gather(self, slot: int, idx: torch.Tensor):
+        out = {}
+        idx = idx.contiguous()
+        for k, src in self.dat.items():
+            dst = self._buf[slot][k][:idx.numel()]
+            L.gather_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), idx.numel(), src.shape[1], dst.data_ptr(),
+                          dst.stride(0))
+            self._tag += 1
+            dst._fxn_tag = self._tag
+            out[k] = dst
+        return out
+
+    def __iter__(self):
+        n = self.valid.numel()
+        perm = self.valid[torch.randperm(n, device=self.device, generator=self.gen)] if self.shuffle else self.valid
+        for b in range(len(self)):
+            a = perm[b * self.batch_size:(b + 1) * self.batch_size]
+            p, q = self.sample_indices(a)
+            yield self._gather(0, a), self._gather(1, p), self._gather(2, q), {k: v[a] for k, v in self.ann.items()}

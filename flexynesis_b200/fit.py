@@ -131,10 +131,14 @@ def fit(model, dataset, batch_size: int, epochs: int, device="cuda", val_dataset
         log_every: int = 0):
     """Train `model` on `dataset` (MultiOmicDataset duck type) with the engine's fused steps. Returns the per-epoch
     history [{'train_loss': ..., 'val_loss': ...}]."""
-    from .data import DeviceBatcher
+    from .data import DeviceBatcher, DeviceTripletBatcher
     model.to(device)
     model.train()
-    loader = DeviceBatcher(dataset, batch_size, device, shuffle=True, drop_last=True, seed=seed)
+    if getattr(model, "main_var", None) is not None:       # MultiTripletNetwork: on-device triplet sampling
+        loader = DeviceTripletBatcher(dataset, model.main_var, batch_size, device, shuffle=True, drop_last=True, seed=seed)
+        loader.full_batch = False
+    else:
+        loader = DeviceBatcher(dataset, batch_size, device, shuffle=True, drop_last=True, seed=seed)
     val = DeviceBatcher(val_dataset, len(val_dataset), device, shuffle=False, drop_last=False) if val_dataset else None
     history = []
     graphed = None

@@ -488,3 +488,40 @@ def test_feature_importance_matches_oracle_attribution():
                 rep.close(f"importance[{var}][class {c}][{layer}]", got, want[c][j] / N)
         assert var in model.feature_importances
     rep.finish()
+
+
+def test_device_triplet_batcher_follows_the_reference_sampling_law():
+    """DeviceTripletBatcher against TripletMultiOmicDataset's rules (data.py:1088-1151):
+    anchors = samples with a label, each once per epoch; positive = another sample of the anchor's class; negative from
+    a different class group (NaN labels form the group "NA"); gathered rows are the dataset's rows, bit for bit."""
+    from flexynesis_b200 import DeviceTripletBatcher
+    g = torch.Generator().manual_seed(0)
+    N = 500
+    lab = torch.randint(0, 4, (N,), generator=g).float()
+    lab[torch.rand(N, generator=g) < 0.1] = float("nan")
+    lab[7] = 9.0                                               # a class with a single member
+    dat = {"a": torch.randn(N, 37, generator=g), "b": torch.randn(N, 12, generator=g)}
+    ds = _DS(dat, {"c": lab}, {"c": "categorical"})
+    ds.ann = {"c": lab}
+    bt = DeviceTripletBatcher(ds, "c", 64, "cuda", seed=1)
+    seen = []
+    labc = lab.cuda()
+    for anchor, pos, neg, y in bt:
+        a_idx = (anchor["a"][:, None, :] == dat["a"].cuda()[None, :, :]).all(-1).float().argmax(1)
+        p_idx = (pos["a"][:, None, :] == dat["a"].cuda()[None, :, :]).all(-1).float().argmax(1)
+        n_idx = (neg["a"][:, None, :] == dat["a"].cuda()[None, :, :]).all(-1).float().argmax(1)
+        assert torch.equal(anchor["b"], dat["b"].cuda()[a_idx]) and torch.equal(pos["b"], dat["b"].cuda()[p_idx])
+        assert torch.equal(y["c"], labc[a_idx])
+        assert not torch.isnan(labc[a_idx]).any()
+        assert torch.equal(labc[p_idx], labc[a_idx])
+        single = labc[a_idx] == 9.0
+        assert bool(((p_idx != a_idx) | single).all())
+        ln = labc[n_idx]
+        assert bool((torch.isnan(ln) | (ln != labc[a_idx])).all())
+        seen.append(a_idx.cpu())
+    seen = torch.cat(seen)
+    assert seen.unique().numel() == seen.numel() == len(bt) * 64
+    # negatives reach every other group, including NA
+    _, q = bt.sample_indices(torch.full((4000,), int(torch.nonzero(lab == 0)[0]), device="cuda"))
+    lq = labc[q]
+    assert bool(torch.isnan(lq).any()) and set(lq[~torch.isnan(lq)].unique().tolist()) == {1.0, 2.0, 3.0, 9.0}
