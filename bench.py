@@ -261,7 +261,7 @@ def run_reference(args, w):
                                    "of the reference's torch CPU path (real Lightning is not installable offline)"},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def measured_traffic(workload: str):
@@ -428,7 +428,7 @@ def run_b200(args, w):
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms_per_step, "launches_per_step": step.launches_per_step}))
+            emit({"profile_run": True, "ms_per_step": ms_per_step, "launches_per_step": step.launches_per_step})
         return
     # ---------------- end-to-end arm (host batch -> device every step, loss read back every step) ----------------
     from flexynesis_b200.fit import HostStreamTrainer
@@ -496,10 +496,22 @@ def run_b200(args, w):
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
             "model_tflops": fl * value / 1e12, "final_loss": final_loss,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -514,6 +526,13 @@ def main():
     ap.add_argument("--profile", action="store_true", help="timed steps only (for ncu launch lists): no e2e/roofline/cpu legs")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    # stdout carries exactly ONE JSON line: file descriptor 1 is pointed at stderr for the life of the process (NCCL prints
+    # its version banner to stdout at every debug level >= VERSION, torchrun children inherit whatever the box exports) and
+    # the result line is written to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, w)
     else:
