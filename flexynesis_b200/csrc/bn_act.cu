@@ -11,6 +11,7 @@
 #include "fxn_internal.h"
 #include "ptx.cuh"
 #include "rng.cuh"
+#include <cstdlib>
 
 namespace fxn {
 
@@ -70,10 +71,12 @@ constexpr int BN_THREADS = 256;
 // MLP encoders; tall inputs (flexGCN normalises B*N = 8 M rows of 32 channels) get fatter blocks so that the grid stays
 // within a few waves of 148 SMs and the per-block prologue / column atomics stay negligible.
 static inline int bn_rows_per_block(long long rows, int col_blocks) {
-  const long long target_blocks = 148LL * 16;
+  static const int min_rows = [] { const char* e = getenv("FXN_BN_MIN_ROWS"); return e ? atoi(e) : BN_ROWS; }();
+  static const int waves = [] { const char* e = getenv("FXN_BN_WAVES"); return e ? atoi(e) : 16; }();
+  const long long target_blocks = 148LL * waves;
   long long rpb = (rows * col_blocks + target_blocks - 1) / target_blocks;
   rpb = (rpb + 31) / 32 * 32;
-  if (rpb < BN_ROWS) rpb = BN_ROWS;
+  if (rpb < min_rows) rpb = min_rows;
   return static_cast<int>(rpb);
 }
 
