@@ -1,0 +1,62 @@
+"""Host-side logic that needs no GPU: the safetensors round trip of the drop-in classes' state_dict (the reference
+saves models that way, flexynesis/__main__.py:1563-1569, and loads them strictly, inference.py:378-379), the
+trials-per-device scheduler, and the tile-width planner of concurrent encoder GEMMs."""
+import os
+
+import pytest
+import torch
+
+import flexynesis_b200 as fx
+from flexynesis_b200.engine import concurrent_tile_widths
+from flexynesis_b200.trials import run_trials
+
+
+class _DS:
+    def __init__(self, dims, ann, vt):
+        self.dat = {f"l{i}": torch.randn(12, d) for i, d in enumerate(dims)}
+        self.ann, self.variable_types = ann, vt
+        self.features = {k: [f"f{j}" for j in range(v.shape[1])] for k, v in self.dat.items()}
+        self.samples = [f"s{i}" for i in range(12)]
+
+
+@pytest.mark.parametrize("cls", ["DirectPred", "supervised_vae", "CrossModalPred"])
+def test_state_dict_round_trips_through_safetensors(tmp_path, cls):
+    from safetensors.torch import load_file, save_file
+    torch.manual_seed(0)
+    ann = {"y": torch.randn(12), "c": torch.tensor([0., 1, 2] * 4)}
+    ds = _DS([40, 30], ann, {"y": "numerical", "c": "categorical"})
+    cfg = {"latent_dim": 8, "hidden_dim_factor": 0.25, "supervisor_hidden_dim": 4, "lr": 1e-3}
+    make = lambda: getattr(fx, cls)(cfg, ds, ["y", "c"], device_type="cpu")
+    a, b = make(), make()
+    path = str(tmp_path / "m.safetensors")
+    save_file(a.state_dict(), path)
+    b.load_state_dict(load_file(path), strict=True)
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+
+
+def _objective(cfg, device):
+    import time
+    time.sleep(0.5)                                           # long enough for every worker to be up and pulling
+    if cfg.get("boom"):
+        raise ValueError("boom")
+    return (cfg["x"] ** 2, device, os.getpid())
+
+
+@pytest.mark.timeout(300)
+def test_run_trials_spreads_trials_over_devices_and_keeps_order():
+    res = run_trials(_objective, [{"x": i} for i in range(7)], devices=["cpu:0", "cpu:1", "cpu:2"], timeout=120)
+    assert [r[0] for r in res] == [i * i for i in range(7)]
+    assert {r[1] for r in res} <= {"cpu:0", "cpu:1", "cpu:2"}
+    assert len({r[2] for r in res}) >= 2                      # really ran in several worker processes
+    with pytest.raises(RuntimeError, match="boom"):
+        run_trials(_objective, [{"x": 1}, {"x": 2, "boom": True}], devices=["cpu:0"], timeout=120)
+
+
+def test_concurrent_tile_widths():
+    assert concurrent_tile_widths(4096, [512], [5000]) == [0]                   # a single branch plans for the whole chip
+    bns = concurrent_tile_widths(4096, [512, 307], [5000, 3000])                # config 2: both branches co-resident
+    assert bns == [256, 160]
+    mt = 4096 // 256
+    assert sum(2 * mt * -(-h // bn) for h, bn in zip([512, 307], bns)) <= 148
+    assert concurrent_tile_widths(32768, [512, 307], [5000, 3000]) == [0, 0]    # no co-resident plan: library default
