@@ -210,8 +210,24 @@ __device__ __forceinline__ void epi_rows(const Gemm2Args& p, const EpiRowCtx& cx
   const float* xptr = mse ? p.mse_x + row0 * p.ldx + cx.col : nullptr;
   __nv_bfloat16* hptr = planes ? p.c_hi + row0 * p.ldp + cx.col : nullptr;
   __nv_bfloat16* lptr = planes ? p.c_lo + row0 * p.ldp + cx.col : nullptr;
-  const float* gra = (act == 7) ? p.gauss_ra : nullptr;
-#pragma unroll 4
+  // Gaussian-kernel epilogue: the row norms of this warp's 32 rows are fetched ONCE per chunk (lane = row) and handed out
+  // by shuffle; a load per loop iteration exposed 16 L2 latencies per chunk (the [4096 x 4096] Gram GEMM ran 6x slower
+  // than a plain-store GEMM of its size).
+  float ra_lane = 0.f;
+  if (act == 7) ra_lane = __ldg(p.gauss_ra + min(cx.mbase + static_cast<int>(threadIdx.x & 31), p.M - 1));
+  // Fused reconstruction error: the 16 target values this lane needs come from HBM (x is read exactly once per step).
+  // Issued one per loop iteration they cost 16 exposed memory latencies per chunk (the Decoder output GEMM ran at 1/6 of
+  // the encoder GEMM's rate, profiles/r01_timeline_cfg3_before_mse_prefetch.log); interior chunks fetch all 16 up front.
+  float2 xt[16];
+  if constexpr (!RT && MSE) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xt[i] = __ldg(reinterpret_cast<const float2*>(xptr + static_cast<long long>(2 * i) * p.ldx));
+  }
+  if constexpr (!RT && CMODE == 2 && !MSE) {      // C += : the old values, same reasoning
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xt[i] = *reinterpret_cast<const float2*>(cptr + static_cast<long long>(2 * i) * p.ldc);
+  }
+#pragma unroll (RT ? 4 : ((MSE || CMODE == 2) ? 16 : 4))
   for (int i = 0; i < 16; ++i) {
     const int r = 2 * i + cx.rr;
     const bool rok = RT ? (r < cx.rows_valid) : true;
@@ -220,7 +236,7 @@ __device__ __forceinline__ void epi_rows(const Gemm2Args& p, const EpiRowCtx& cx
     x.x = fmaf(x.x, cx.alpha, cx.b0);
     x.y = fmaf(x.y, cx.alpha, cx.b1);
     if (act == 7) {
-      const float ra = __ldg(gra + (RT ? min(cx.mbase + r, p.M - 1) : cx.mbase + r));
+      const float ra = __shfl_sync(0xffffffffu, ra_lane, r);
       x.x = __expf(-fmaxf(ra + cx.rb0 - 2.f * x.x, 0.f) * p.gauss_inv);
       x.y = __expf(-fmaxf(ra + cx.rb1 - 2.f * x.y, 0.f) * p.gauss_inv);
     } else if (act == 1) {
@@ -238,7 +254,8 @@ __device__ __forceinline__ void epi_rows(const Gemm2Args& p, const EpiRowCtx& cx
         if (ok1) atomicAdd(cp_ + 1, x.y);
       } else if (!RT || (ok1 && cx.c_vec2)) {
         float2 o = x;
-        if (cmode == 2) { const float2 old = *reinterpret_cast<const float2*>(cp_); o.x += old.x; o.y += old.y; }
+        if constexpr (!RT && CMODE == 2 && !MSE) { o.x += xt[i].x; o.y += xt[i].y; }
+        else if (cmode == 2) { const float2 old = *reinterpret_cast<const float2*>(cp_); o.x += old.x; o.y += old.y; }
         *reinterpret_cast<float2*>(cp_) = o;
       } else {
         if (ok0) cp_[0] = cmode == 2 ? cp_[0] + x.x : x.x;
@@ -250,7 +267,8 @@ __device__ __forceinline__ void epi_rows(const Gemm2Args& p, const EpiRowCtx& cx
       float t0 = 0.f, t1 = 0.f;
       if (rok) {
         const float* xp = xptr + static_cast<long long>(2 * i) * p.ldx;
-        if (!RT || (ok1 && cx.x_vec2)) { const float2 t = __ldg(reinterpret_cast<const float2*>(xp)); t0 = t.x; t1 = t.y; }
+        if constexpr (!RT) { t0 = xt[i].x; t1 = xt[i].y; (void)xp; }
+        else if (ok1 && cx.x_vec2) { const float2 t = __ldg(reinterpret_cast<const float2*>(xp)); t0 = t.x; t1 = t.y; }
         else { if (ok0) t0 = __ldg(xp); if (ok1) t1 = __ldg(xp + 1); }
       }
       const float d0 = (rok && ok0) ? x.x - t0 : 0.f, d1 = (rok && ok1) ? x.y - t1 : 0.f;

@@ -713,9 +713,10 @@ class TrunkEngine(EngineBase):
         # ONCE here, on a stream beside the forward pass, instead of by ~15 small memset nodes on the backward critical path
         pz = self.sync is None and self.parallel_encoders
         zk = len(self.aux) - 1
-        if pz:
-            self._aux_run(zk, lambda: (self.arena.grad.zero_(), torch._foreach_zero_(ws["_zero"])))
+        step_start = self._mark()
         self.trunk_forward(ws, True, masks)
+        if pz:       # depends on the start of the step only, but is QUEUED behind the forward GEMMs so that they get the SMs first
+            self._aux_run(zk, lambda: (self.arena.grad.zero_(), torch._foreach_zero_(ws["_zero"])), after=step_start)
         Fa = ws["F_p"].rows_view(0, B)
         self.heads.forward(hw, Fa, B, y, True, masks)
         if self.G == 3:
@@ -977,8 +978,13 @@ class VAEEngine(EngineBase):
             L.randn(ws["eps"].data_ptr(), Lp, B, Lt, self.seed + 11, a.step.data_ptr())
         L.reparam_fwd(ws["mean"].data_ptr(), ws["s"].data_ptr(), ws["eps"].data_ptr(), Lp, B, Lt, ws["z"].data_ptr(),
                       ws["z_p"])
-        # decoders, and beside them (aux stream) the heads and the MMD chain
+        # decoders, and beside them (aux stream) the heads and the MMD chain. The aux chain is queued FIRST: the Decoder
+        # output GEMMs are persistent kernels that take every SM's shared memory, and kernels queued behind them on another
+        # stream wait until they retire (the Cox and Gram kernels used to start after both decoders had finished); queued
+        # ahead, the short chain runs on a few SMs while the GEMM's CTA pairs fill the others as they become free.
         self._fork()
+        with torch.cuda.stream(self._aux_stream()):
+            self._heads_and_mmd(ws, y, train, noise, with_loss)
         for i in range(nd):
             with torch.cuda.stream(self._stream_for(i)):
                 self._hidden_fwd(ws, "d", i, f"decoders.{i}", ws["z_p"], Lt, self.wp(self.wd[i]), train)
@@ -992,8 +998,6 @@ class VAEEngine(EngineBase):
                        mse_x=x.data_ptr(), ldx=x.stride(0), mse_acc=fptr(ws["mse_acc"], i),
                        colstats=a.g(f"decoders.{i}.FC_output.bias") if train else None, stats_mode=3,
                        stats_alpha=scale, stats_alpha_dev=w_mmd)
-        with torch.cuda.stream(self._aux_stream()):
-            self._heads_and_mmd(ws, y, train, noise, with_loss)
         self._join()
         if with_loss:
             L.mmd_finish(ws["cs_zz"].data_ptr(), ws["cs_tt"].data_ptr(), ws["cs_tz"].data_ptr(),
