@@ -244,7 +244,9 @@ __device__ __forceinline__ void epi_rows(const Gemm2Args& p, const EpiRowCtx& cx
     } else if (act == 6) {
       x.x = x.x > 0.f ? x.x : 0.2f * x.x; x.y = x.y > 0.f ? x.y : 0.2f * x.y;
     } else if (act == 3) {
-      x.x = 1.f / (1.f + __expf(-x.x)); x.y = 1.f / (1.f + __expf(-x.y));
+      // approximate reciprocal (MUFU.RCP, ~1 ulp): an IEEE division costs ~10 dependent instructions per element and the
+      // epilogue runs one warp per scheduler, so dependent-instruction count is what its time is made of
+      x.x = __fdividef(1.f, 1.f + __expf(-x.x)); x.y = __fdividef(1.f, 1.f + __expf(-x.y));
     }
     if (RT) { if (!ok0) x.x = 0.f; if (!ok1) x.y = 0.f; }
     if (cmode != 0 && rok) {
