@@ -214,12 +214,14 @@ def cpu_model_name() -> str:
     return "unknown"
 
 
-def cpu_reference_steps(w, steps, warmup, threads, budget_s: float = 60.0):
+def cpu_reference_steps(w, steps, warmup, threads, budget_s: float = 60.0, batch_rows: int = 0):
     """The reference's CPU training step (oracle port: same torch ops as flexynesis/modules.py + models/*.py +
     Lightning's clip/Adam policy) on a pre-collated batch with all host threads. Stops early once `budget_s` of timed
     work has been done (bounded sample)."""
     from oracle.restatement import Trainer, init_params, synthetic_batch
     torch.set_num_threads(threads)
+    if batch_rows:
+        w = dict(w, B=batch_rows)
     spec = make_spec(w)
     torch.manual_seed(0)
     P = init_params(spec)
@@ -489,6 +491,10 @@ def run_b200(args, w):
             cpu_base = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "cpu": cpu_model_name(),
                         "sample": f"{done} full-batch steps (B={B}) after 2 warm-up, pre-collated batch, "
                                   f"{per * 1e3:.1f} ms/step, torch threads = {threads}"}
+            if B > 128:      # also at the reference's default maximum batch size (main.py:183-190)
+                s128, p128, d128 = cpu_reference_steps(w, 200, 3, threads, budget_s=6.0, batch_rows=128)
+                cpu_base["at_reference_default_batch"] = {"batch": 128, "value": s128, "unit": "samples/s",
+                                                          "ms_per_step": p128 * 1e3, "steps": d128}
         fl = train_flops_per_sample(w)
         line = {
             "metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
