@@ -228,11 +228,12 @@ def head_out_fwd(D, ldd, rows, sh, W, bias, Cc, logits, ldl, kind, y, acc) -> No
                                C.c_void_p(acc), C.c_void_p(stream())), "fxn_head_out_fwd")
 
 
-def head_out_bwd(D, ldd, rows, sh, W, Cc, logits, ldl, kind, y, acc, coef, weight, dD, ldg, dW, dbias) -> None:
+def head_out_bwd(D, ldd, rows, sh, W, Cc, logits, ldl, kind, y, acc, coef, weight, dD, ldg, dW, dbias,
+                 prezeroed: bool = False) -> None:
     check(lib.fxn_head_out_bwd(C.c_void_p(D), c_ll(ldd), C.c_int(rows), C.c_int(sh), C.c_void_p(W), C.c_int(Cc),
                                C.c_void_p(logits), c_ll(ldl), C.c_int(kind), C.c_void_p(y), C.c_void_p(acc),
                                C.c_void_p(coef), C.c_void_p(weight), C.c_void_p(dD), c_ll(ldg), C.c_void_p(dW),
-                               C.c_void_p(dbias), C.c_void_p(stream())), "fxn_head_out_bwd")
+                               C.c_void_p(dbias), C.c_int(int(prezeroed)), C.c_void_p(stream())), "fxn_head_out_bwd")
 
 
 def cox_fwd(o, ldo, durations, events, n, coef, acc) -> None:

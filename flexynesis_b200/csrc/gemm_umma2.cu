@@ -227,12 +227,21 @@ __device__ __forceinline__ void epi_rows(const Gemm2Args& p, const EpiRowCtx& cx
 #pragma unroll
     for (int i = 0; i < 16; ++i) xt[i] = *reinterpret_cast<const float2*>(cptr + static_cast<long long>(2 * i) * p.ldc);
   }
-#pragma unroll (RT ? 4 : ((MSE || CMODE == 2) ? 16 : 4))
+  // Interior chunks read their 16 staged values up front: the epilogue runs ONE warp per scheduler, so every
+  // shared-memory load left inside the loop is an exposed latency (the loads are volatile asm and are not hoisted by
+  // the compiler); with the values in registers the 16 iterations are independent instruction streams.
+  float2 xin[16];
+  if constexpr (!RT) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xin[i] = lds_f2(cx.stg + 2 * i * G2_STG_LD * 4);
+  }
+#pragma unroll (RT ? 4 : 16)
   for (int i = 0; i < 16; ++i) {
     const int r = 2 * i + cx.rr;
     const bool rok = RT ? (r < cx.rows_valid) : true;
     const bool ok0 = RT ? cx.ok0 : true, ok1 = RT ? cx.ok1 : true;
-    float2 x = lds_f2(cx.stg + 2 * i * G2_STG_LD * 4);
+    float2 x;
+    if constexpr (RT) x = lds_f2(cx.stg + 2 * i * G2_STG_LD * 4); else x = xin[i];
     x.x = fmaf(x.x, cx.alpha, cx.b0);
     x.y = fmaf(x.y, cx.alpha, cx.b1);
     if (act == 7) {

@@ -396,7 +396,7 @@ extern "C" int fxn_head_out_fwd(const float* D, long long ldd, int rows, int sh,
 extern "C" int fxn_head_out_bwd(const float* D, long long ldd, int rows, int sh, const float* W, int C,
                                 const float* logits, long long ldl, int kind, const float* y, const float* acc,
                                 const float* coef, const float* weight, float* dD, long long ldg, float* dW,
-                                float* dbias, void* stream_) {
+                                float* dbias, int prezeroed, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!D || !W || !logits || !dD || !dW) return set_error(FXN_ERR_ARG, "fxn_head_out_bwd: null argument");
   if (C > MAX_CLASSES) return set_error(FXN_ERR_UNSUPPORTED, "fxn_head_out_bwd: more than %d classes", MAX_CLASSES);
@@ -407,9 +407,11 @@ extern "C" int fxn_head_out_bwd(const float* D, long long ldd, int rows, int sh,
     cudaError_t e = cudaFuncSetAttribute(head_out_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "head_out_bwd attr: %s", cudaGetErrorString(e));
   }
-  cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * C * sh, stream);
-  if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, sizeof(float) * C, stream);
-  if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "head_out_bwd memset: %s", cudaGetErrorString(e));
+  if (!prezeroed) {
+    cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * C * sh, stream);
+    if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, sizeof(float) * C, stream);
+    if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "head_out_bwd memset: %s", cudaGetErrorString(e));
+  }
   int blocks = ceil_div(rows, HEAD_WARPS * 2);
   if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;

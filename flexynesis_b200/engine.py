@@ -267,12 +267,17 @@ class HeadsBlock:
         if not self.vars:
             return
         model = eng.model
-        # gather the layer_1 biases into the concatenated vector (device-to-device copies of sh floats)
-        for i, v in enumerate(self.vars):
-            self.b1cat[i * self.shp:i * self.shp + self.sh].copy_(a.view(f"MLPs.{v}.layer_1.bias"))
+        # the layer_1 biases as one concatenated vector: a single head whose width needs no padding reads its bias in
+        # place; otherwise they are gathered (device-to-device copies of sh floats)
+        if len(self.vars) == 1 and self.shp == self.sh:
+            b1_ptr = a.p(f"MLPs.{self.vars[0]}.layer_1.bias")
+        else:
+            for i, v in enumerate(self.vars):
+                self.b1cat[i * self.shp:i * self.shp + self.sh].copy_(a.view(f"MLPs.{v}.layer_1.bias"))
+            b1_ptr = self.b1cat.data_ptr()
         mt = L.stat_tiles(B)
         L.gemm(B, self.width, self.L, Fp, 0, self.w1_planes(), 0, C_ptr=ws["Zh"].data_ptr(), ldc=ws["Zh"].stride(0),
-               bias=self.b1cat.data_ptr(), colstats=ws["partials"].data_ptr() if train else None, stats_mode=2)
+               bias=b1_ptr, colstats=ws["partials"].data_ptr() if train else None, stats_mode=2)
         for i, v in enumerate(self.vars):
             mlp = model.MLPs[v]
             c0 = i * self.shp
@@ -350,7 +355,7 @@ class HeadsBlock:
                            y[v].data_ptr() if kind in (1, 2) else None, fptr(ws["acc"], 2 * slot),
                            ws["coef"].data_ptr() if kind == 3 else None, self.weight_ptr(ws, v),
                            fptr(ws["dDh"], c0), ws["dDh"].stride(0), a.g(f"MLPs.{v}.layer_out.weight"),
-                           a.g(f"MLPs.{v}.layer_out.bias") if has_b else None)
+                           a.g(f"MLPs.{v}.layer_out.bias") if has_b else None, prezeroed=prezeroed)
             mask = None if masks is None else masks.get(f"MLPs.{v}.dropout")
             dz = ws["dZh"].cols_view(c0, self.sh)
             eng.bn_backward(V=fptr(ws["Zh"], c0), ldv=ws["Zh"].stride(0), dOut=fptr(ws["dDh"], c0),

@@ -160,10 +160,10 @@ int fxn_col_stats(const float* V, long long ldv, long long rows, int cols, int t
 int fxn_head_out_fwd(const float* D, long long ldd, int rows, int sh, const float* W, const float* bias, int C,
                      float* logits, long long ldl, int kind, const float* y, float* acc, void* stream);
 /* Backward: dlogits from (kind, y, acc[1], *weight) or from Cox coefficients (kind 3), then dD[rows x sh] (stored),
- * dW[C x sh] and dbias[C] (zeroed by the call, accumulated). */
+ * dW[C x sh] and dbias[C] (accumulated with atomics; zeroed by the call unless `prezeroed`: the caller cleared them). */
 int fxn_head_out_bwd(const float* D, long long ldd, int rows, int sh, const float* W, int C, const float* logits,
                      long long ldl, int kind, const float* y, const float* acc, const float* coef,
-                     const float* weight, float* dD, long long ldg, float* dW, float* dbias, void* stream);
+                     const float* weight, float* dD, long long ldg, float* dW, float* dbias, int prezeroed, void* stream);
 /* Cox partial-likelihood loss of risk scores o[n] (stride ldo) -- cox_ph_loss, modules.py:265-305: rows with NaN
  * duration/event dropped, sorted by duration descending, loss = -(sum_{e=1} o_i - log cumsum exp(o))/sum e, 0 when
  * empty or non-finite. acc[0] = loss, acc[1] = 1; coef[n] = d loss / d o. */
