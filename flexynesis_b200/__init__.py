@@ -8,6 +8,7 @@ include/flexynesis_b200.h); the import fails loudly when the library has not bee
 from . import _lib  # noqa: F401  (loads the shared library or raises)
 from .models import CrossModalPred, DirectPred, GNN, MultiTripletNetwork, supervised_vae  # noqa: F401
 from .data import DeviceBatcher, DeviceTripletBatcher, SyntheticMultiOmicDataset  # noqa: F401
+from . import fit, parallel, trials  # noqa: F401,E402
 
 __all__ = ["CrossModalPred", "DirectPred", "GNN", "MultiTripletNetwork", "supervised_vae", "SyntheticMultiOmicDataset", "DeviceBatcher", "DeviceTripletBatcher"]
 __version__ = "0.1.0"
