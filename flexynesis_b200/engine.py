@@ -860,12 +860,15 @@ class VAEEngine(EngineBase):
             for i in range(n):
                 wp.add_segment(f"{name}.weight", i * Lt, Lt, Lt, n * Lt, off + i * Lp, n * Lp)
             self.wfc_off[name] = off
-        self._finish_init(max(n, nd))  # modality streams + one for the heads / MMD chain
+        self._finish_init(max(n, nd) + 1)  # modality streams + one for the heads chain + one for the MMD chain
         self.dims_dev = torch.tensor(self.dd, dtype=torch.int32, device=self.device)
         self.mmd_slot = self.heads.loss_names.index("mmd_loss")
 
     def _aux_stream(self):
         return self.side[-1] if self.parallel_encoders else torch.cuda.current_stream()
+
+    def _mmd_stream(self):
+        return self.side[-2] if self.parallel_encoders else torch.cuda.current_stream()
 
     def wfc(self, name: str, i: Optional[int] = None) -> Planes:
         full = self.wplanes.planes(self.wfc_off[name], self.latent, self.n * self.Lp, self.n * self.Lp)
@@ -988,8 +991,11 @@ class VAEEngine(EngineBase):
         # stream wait until they retire (the Cox and Gram kernels used to start after both decoders had finished); queued
         # ahead, the short chain runs on a few SMs while the GEMM's CTA pairs fill the others as they become free.
         self._fork()
-        with torch.cuda.stream(self._aux_stream()):
-            self._heads_and_mmd(ws, y, train, noise, with_loss)
+        with torch.cuda.stream(self._aux_stream()):          # heads (incl. the single-CTA Cox sort, ~0.1 ms at B = 4096)
+            self.heads.forward(hw, ws["z_p"], B, y, train, noise, with_loss=with_loss)
+        if with_loss:
+            with torch.cuda.stream(self._mmd_stream()):      # Gram GEMMs of the MMD term: independent of the heads
+                self._mmd_forward(ws, train, noise)
         for i in range(nd):
             with torch.cuda.stream(self._stream_for(i)):
                 self._hidden_fwd(ws, "d", i, f"decoders.{i}", ws["z_p"], Lt, self.wp(self.wd[i]), train)
@@ -1009,30 +1015,28 @@ class VAEEngine(EngineBase):
                          ws["mse_acc"].data_ptr(), self.dims_dev.data_ptr(), nd, B, P, fptr(hw["acc"], 2 * self.mmd_slot))
             hb.total(hw)
 
-    def _heads_and_mmd(self, ws, y, train, noise, with_loss):
-        a, hw, hb = self.arena, ws["heads"], self.heads
+    def _mmd_forward(self, ws, train, noise):
+        a = self.arena
         B, n, Lt, Lp, P = ws["B"], self.nd, self.latent, self.Lp, self.PRIOR      # n: decoded layers
-        hb.forward(hw, ws["z_p"], B, y, train, noise, with_loss=with_loss)
-        if with_loss:
-            # MMD: Gaussian-kernel Gram matrices + column sums
-            inv = 1.0 / (float(Lt) * float(Lt))
-            L.row_sqnorm(ws["z"].data_ptr(), Lp, B, Lt, ws["rz"].data_ptr())
-            L.gemm(B, B, Lt, ws["z_p"], 0, ws["z_p"], 0, out=ws["Kzz_p"], epi_act=7, gauss_ra=ws["rz"].data_ptr(),
-                   gauss_rb=ws["rz"].data_ptr(), gauss_inv=inv, colstats=ws["cs_zz"].data_ptr(), stats_mode=3)
-            for i in range(n):
-                T = ws["T"][i]
-                if f"mmd_prior.{i}" in noise:
-                    T[:, :Lt].copy_(noise[f"mmd_prior.{i}"])
-                else:
-                    L.randn(T.data_ptr(), Lp, P, Lt, self.seed + 101 + i, a.step.data_ptr())
-                L.split_planes(T[:, :Lt], ws["T_p"][i])
-                L.row_sqnorm(T.data_ptr(), Lp, P, Lt, ws["rt"][i].data_ptr())
-                L.gemm(P, B, Lt, ws["T_p"][i], 0, ws["z_p"], 0, out=ws["Ktz_p"][i], epi_act=7,
-                       gauss_ra=ws["rt"][i].data_ptr(), gauss_rb=ws["rz"].data_ptr(), gauss_inv=inv,
-                       colstats=ws["cs_tz"][i].data_ptr(), stats_mode=3)
-                L.gemm(P, P, Lt, ws["T_p"][i], 0, ws["T_p"][i], 0, out=ws["Ktt_p"], epi_act=7,
-                       gauss_ra=ws["rt"][i].data_ptr(), gauss_rb=ws["rt"][i].data_ptr(), gauss_inv=inv,
-                       colstats=ws["cs_tt"][i].data_ptr(), stats_mode=3)
+        # MMD: Gaussian-kernel Gram matrices + column sums
+        inv = 1.0 / (float(Lt) * float(Lt))
+        L.row_sqnorm(ws["z"].data_ptr(), Lp, B, Lt, ws["rz"].data_ptr())
+        L.gemm(B, B, Lt, ws["z_p"], 0, ws["z_p"], 0, out=ws["Kzz_p"], epi_act=7, gauss_ra=ws["rz"].data_ptr(),
+               gauss_rb=ws["rz"].data_ptr(), gauss_inv=inv, colstats=ws["cs_zz"].data_ptr(), stats_mode=3)
+        for i in range(n):
+            T = ws["T"][i]
+            if f"mmd_prior.{i}" in noise:
+                T[:, :Lt].copy_(noise[f"mmd_prior.{i}"])
+            else:
+                L.randn(T.data_ptr(), Lp, P, Lt, self.seed + 101 + i, a.step.data_ptr())
+            L.split_planes(T[:, :Lt], ws["T_p"][i])
+            L.row_sqnorm(T.data_ptr(), Lp, P, Lt, ws["rt"][i].data_ptr())
+            L.gemm(P, B, Lt, ws["T_p"][i], 0, ws["z_p"], 0, out=ws["Ktz_p"][i], epi_act=7,
+                   gauss_ra=ws["rt"][i].data_ptr(), gauss_rb=ws["rz"].data_ptr(), gauss_inv=inv,
+                   colstats=ws["cs_tz"][i].data_ptr(), stats_mode=3)
+            L.gemm(P, P, Lt, ws["T_p"][i], 0, ws["T_p"][i], 0, out=ws["Ktt_p"], epi_act=7,
+                   gauss_ra=ws["rt"][i].data_ptr(), gauss_rb=ws["rt"][i].data_ptr(), gauss_inv=inv,
+                   colstats=ws["cs_tt"][i].data_ptr(), stats_mode=3)
 
     def forward_backward(self, x_groups, y, masks=None):
         x_list = x_groups[0]
