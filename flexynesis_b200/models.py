@@ -551,6 +551,52 @@ class supervised_vae(_EngineModel):
             outs.append(self.forward([x[i] for x in inputs])[4][target_var])
         return torch.cat(outs, dim=0)
 
+    def compute_feature_importance(self, dataset, target_var, method="IntegratedGradients", steps_or_samples=5,
+                                   batch_size=512):
+        """Mean |attribution| per feature, class and (input) layer with the reference's DataFrame layout
+        (supervised_vae.py / crossmodal_pred.py `compute_feature_importance`). The integrand is evaluated with torch
+        autograd on the container modules (any device) -- this model family's attribution is not an engine path; only
+        captum's quadrature (`attribution_path`) is restated. As in the reference the latent code is re-drawn at every
+        path point (`reparameterization` has no eval branch)."""
+        device = _resolve_device(self.device_type)
+        was_training = self.training
+        self.to(device)
+        self.eval()
+        layers = list(self.layers)
+        n = len(dataset.samples) if hasattr(dataset, "samples") else next(iter(dataset.dat.values())).shape[0]
+        if dataset.variable_types[target_var] == "numerical":
+            num_class = 1
+        else:
+            num_class = len(np.unique(np.asarray(dataset.ann[target_var], dtype=np.float64)))
+        alphas, weights = attribution_path(method, steps_or_samples)
+        sums = [[torch.zeros(len(dataset.features[k]), dtype=torch.float64) for k in layers] for _ in range(num_class)]
+        for s in range(0, n, batch_size):
+            xs = [torch.as_tensor(dataset.dat[k][s:s + batch_size]).to(device, torch.float32) for k in layers]
+            for cls in range(num_class):
+                G = [torch.zeros_like(x) for x in xs]
+                for al, w in zip(alphas, weights):
+                    xk = [(x * float(al)).detach().requires_grad_(True) for x in xs]
+                    out = self.forward(xk)[4][target_var]
+                    grads = torch.autograd.grad(out[:, cls].sum(), xk)
+                    for g, d in zip(G, grads):
+                        g += float(w) * d
+                for j, (x, g) in enumerate(zip(xs, G)):
+                    sums[cls][j] += (x * g).abs().sum(0).double().cpu()
+        self.to("cpu")
+        if was_training:
+            self.train()
+        mappings = getattr(dataset, "label_mappings", {}) or {}
+        frames = []
+        for i in range(num_class):
+            for j, k in enumerate(layers):
+                label = mappings[target_var].get(i) if target_var in mappings else ""
+                frames.append(pd.DataFrame({"target_variable": target_var, "target_class": i, "target_class_label": label,
+                                            "layer": k, "name": dataset.features[k],
+                                            "importance": (sums[i][j] / n).float().numpy()}))
+        df = pd.concat(frames, ignore_index=True)
+        self.feature_importances[target_var] = df
+        return df
+
 
 class CrossModalPred(supervised_vae):
     """Cross-modality VAE (flexynesis/models/crossmodal_pred.py:31-187): Encoders over `input_layers`, Decoders into

@@ -60,3 +60,34 @@ def test_concurrent_tile_widths():
     mt = 4096 // 256
     assert sum(2 * mt * -(-h // bn) for h, bn in zip([512, 307], bns)) <= 148
     assert concurrent_tile_widths(32768, [512, 307], [5000, 3000]) == [0, 0]    # no co-resident plan: library default
+
+
+def test_vae_feature_importance_satisfies_completeness():
+    """supervised_vae / CrossModalPred attribution (torch path): with a deterministic latent code (FC_log_var zeroed, so
+    z = mean) Integrated Gradients must satisfy completeness -- sum over features of the signed attributions equals
+    f(x) - f(0) per sample -- which the quadrature reaches at 64 Gauss-Legendre points; and the returned frame has the
+    reference's layout."""
+    from flexynesis_b200.models import attribution_path
+    torch.manual_seed(0)
+    ann = {"y": torch.randn(12), "c": torch.tensor([0., 1, 2] * 4)}
+    ds = _DS([40, 30], ann, {"y": "numerical", "c": "categorical"})
+    cfg = {"latent_dim": 8, "hidden_dim_factor": 0.25, "supervisor_hidden_dim": 4, "lr": 1e-3}
+    m = fx.CrossModalPred(cfg, ds, ["y", "c"], input_layers=["l0"], output_layers=["l1"], device_type="cpu")
+    with torch.no_grad():
+        m.FC_log_var.weight.zero_(); m.FC_log_var.bias.zero_()
+    m.eval()
+    df = m.compute_feature_importance(ds, "c", steps_or_samples=8, batch_size=5)
+    assert list(df.columns) == ["target_variable", "target_class", "target_class_label", "layer", "name", "importance"]
+    assert len(df) == 3 * 40 and set(df.layer) == {"l0"} and (df.importance >= 0).all()
+    # completeness, straight from the definition
+    x = ds.dat["l0"]
+    alphas, weights = attribution_path("IntegratedGradients", 64)
+    G = torch.zeros_like(x)
+    for al, w in zip(alphas, weights):
+        xk = (x * float(al)).requires_grad_(True)
+        out = m.forward([xk])[4]["y"]
+        G += float(w) * torch.autograd.grad(out[:, 0].sum(), [xk])[0]
+    with torch.no_grad():
+        f1 = m.forward([x])[4]["y"][:, 0]
+        f0 = m.forward([torch.zeros_like(x)])[4]["y"][:, 0]
+    assert torch.allclose((x * G).sum(1), f1 - f0, atol=2e-3), ((x * G).sum(1) - (f1 - f0)).abs().max()
