@@ -247,6 +247,41 @@ def cpu_reference_steps(w, steps, warmup, threads, budget_s: float = 60.0, batch
     return w["B"] * done / dt, dt / done, done
 
 
+def cpu_reference_with_dataloader(w, threads, max_batches: int = 3):
+    """The same CPU step fed the way the reference feeds it (flexynesis/main.py:289-298): a torch DataLoader
+    (shuffle, drop_last, num_workers = 0) over a map-style dataset whose __getitem__ returns ({layer: row}, {var: label},
+    name) and default_collate stacking B samples per batch (data.py:980-995). Bounded sample: `max_batches` batches of
+    a dataset two batches long. Returns samples/s, or None for the graph workload (different dataset class)."""
+    if w["model"] == "GNN":
+        return None
+    import flexynesis_b200 as fx
+    from torch.utils.data import DataLoader
+    from oracle.restatement import Trainer, init_params
+    torch.set_num_threads(threads)
+    spec = make_spec(w)
+    surv = w.get("surv", (None, None))
+    vt = {v: VT[v] for v in w["vars"]}
+    if surv[1]:
+        vt[surv[1]] = "numerical"
+    ds = fx.SyntheticMultiOmicDataset(w["dims"], 2 * w["B"], vt, w["classes"], surv_event_var=surv[0], surv_time_var=surv[1],
+                                      seed=0)
+    torch.manual_seed(0)
+    tr = Trainer(init_params(spec), spec, 1e-3)
+    loader = DataLoader(ds, batch_size=w["B"], shuffle=True, drop_last=True, num_workers=0)
+    done, t0 = 0, None
+    while done < max_batches:
+        for dat, y, _ in loader:
+            if t0 is None:                      # first batch = warm-up of the step; the clock starts after it
+                tr.step((dat, y, None))
+                t0 = time.perf_counter()
+                continue
+            tr.step((dat, y, None))
+            done += 1
+            if done >= max_batches:
+                break
+    return w["B"] * done / (time.perf_counter() - t0)
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -491,6 +526,14 @@ def run_b200(args, w):
             cpu_base = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "cpu": cpu_model_name(),
                         "sample": f"{done} full-batch steps (B={B}) after 2 warm-up, pre-collated batch, "
                                   f"{per * 1e3:.1f} ms/step, torch threads = {threads}"}
+            try:             # step-only above, and with the reference's DataLoader + default_collate
+                wl = cpu_reference_with_dataloader(w, threads)
+                if wl is not None:
+                    cpu_base["with_reference_dataloader"] = {"value": wl, "unit": "samples/s",
+                                                             "sample": "3 batches after 1 warm-up; per-sample __getitem__ + "
+                                                                       "default_collate, shuffle, drop_last, num_workers=0"}
+            except Exception as e:      # never lose the bench line over the secondary baseline
+                cpu_base["with_reference_dataloader"] = {"error": f"{type(e).__name__}: {e}"[:160]}
             if B > 128:      # also at the reference's default maximum batch size (main.py:183-190)
                 s128, p128, d128 = cpu_reference_steps(w, 200, 3, threads, budget_s=6.0, batch_rows=128)
                 cpu_base["at_reference_default_batch"] = {"batch": 128, "value": s128, "unit": "samples/s",
