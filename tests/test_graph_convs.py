@@ -64,3 +64,29 @@ def test_state_dict_keys_follow_pyg():
         flexGCN(10, 2, 8, 4, conv=None)
     with pytest.raises(NotImplementedError):
         flexGCN(10, 2, 8, 4, conv="GAT")
+
+
+@pytest.mark.parametrize("conv", ["GCN", "GC", "SAGE"])
+def test_engine_csr_matches_the_dense_operator(conv):
+    """engine.build_gcn_csr (host logic that feeds the aggregate kernels): the CSR by destination and the CSR by source
+    must both encode the dense operator A[dst, src] = sum of edge weights that the torch containers apply, including
+    duplicate edges, self loops, isolated nodes and (GCN) the added self loops."""
+    from flexynesis_b200.containers import CONVS
+    from flexynesis_b200.engine import build_gcn_csr
+    n = 23
+    ei = _graph(n, 40, 3)
+    ei = ei[:, (ei[0] < n) & (ei[1] < n)]
+    (rp_in, col_in, w_in), (rp_out, col_out, w_out) = build_gcn_csr(ei, n, "cpu", conv)
+    if conv == "GCN":
+        src, dst, w = CONVS[conv].normalized_edges(ei, n)
+    else:
+        src, dst, w = CONVS[conv].edge_weights(ei, n)
+    dense = torch.zeros(n, n).index_put_((dst, src), w, accumulate=True)
+    a_in, a_out = torch.zeros(n, n), torch.zeros(n, n)
+    for v in range(n):
+        for e in range(int(rp_in[v]), int(rp_in[v + 1])):
+            a_in[v, int(col_in[e])] += float(w_in[e])
+        for e in range(int(rp_out[v]), int(rp_out[v + 1])):
+            a_out[int(col_out[e]), v] += float(w_out[e])
+    assert torch.allclose(a_in, dense, atol=1e-6) and torch.allclose(a_out, dense, atol=1e-6)
+    assert int(rp_in[-1]) == int(rp_out[-1]) == src.numel()
