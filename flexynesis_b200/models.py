@@ -741,6 +741,56 @@ class GNN(_EngineModel):
     def forward(self, x, edge_index=None):
         return self._embed(x, edge_index)[1]
 
+    def forward_target(self, *args):
+        """captum adaptor (gnn_early.py:428-438): args = (x[steps, B, N, F], target_var, steps)."""
+        x, target_var, steps = args[0], args[-2], args[-1]
+        return torch.cat([self.forward(x[i])[target_var] for i in range(steps)], dim=0)
+
+    def compute_feature_importance(self, dataset, target_var, method="IntegratedGradients", steps_or_samples=5,
+                                   batch_size=512):
+        """Mean |attribution| per gene, class and omics layer with the reference's DataFrame layout (gnn_early.py:440-633:
+        one row per (class, layer = node-feature column, gene)). The path integral runs through torch autograd on the
+        container modules (contract safety; not an engine path), with captum's quadrature (`attribution_path`)."""
+        device = _resolve_device(self.device_type)
+        was_training = self.training
+        self.to(device)
+        self.eval()
+        if dataset.variable_types[target_var] == "numerical":
+            num_class = 1
+        else:
+            num_class = len(np.unique(np.asarray(dataset.ann[target_var], dtype=np.float64)))
+        alphas, weights = attribution_path(method, steps_or_samples)
+        sums, n = [None] * num_class, 0
+        for x, _ in self._node_batches(dataset, batch_size):
+            x = x.to(device, torch.float32)
+            n += x.shape[0]
+            for cls in range(num_class):
+                G = torch.zeros_like(x)
+                for al, w in zip(alphas, weights):
+                    xk = (x * float(al)).detach().requires_grad_(True)
+                    out = self.forward(xk)[target_var]
+                    G += float(w) * torch.autograd.grad(out[:, cls].sum(), [xk])[0]
+                red = (x * G).abs().sum(0).double().cpu()                      # [N, F]
+                sums[cls] = red if sums[cls] is None else sums[cls] + red
+        self.to("cpu")
+        if was_training:
+            self.train()
+        layers = list(getattr(dataset, "multiomic_dataset", dataset).dat.keys()) if hasattr(
+            getattr(dataset, "multiomic_dataset", dataset), "dat") else [f"layer{j}" for j in range(sums[0].shape[1])]
+        genes = getattr(dataset, "common_features", None) or [f"node{j}" for j in range(sums[0].shape[0])]
+        mappings = getattr(dataset, "label_mappings", {}) or {}
+        frames = []
+        for i in range(num_class):
+            imp = (sums[i] / n).float().numpy()
+            label = mappings[target_var].get(i) if target_var in mappings else ""
+            for j, layer in enumerate(layers):
+                frames.append(pd.DataFrame({"target_variable": target_var, "target_class": i, "target_class_label": label,
+                                            "layer": layer, "name": genes,
+                                            "importance": imp[:, j] if imp.shape[1] > 1 else imp[:, 0]}))
+        df = pd.concat(frames, ignore_index=True)
+        self.feature_importances[target_var] = df
+        return df
+
     def _node_batches(self, dataset, batch_size):
         n = len(dataset)
         feats = getattr(dataset, "node_features_tensor", None)

@@ -91,3 +91,43 @@ def test_vae_feature_importance_satisfies_completeness():
         f1 = m.forward([x])[4]["y"][:, 0]
         f0 = m.forward([torch.zeros_like(x)])[4]["y"][:, 0]
     assert torch.allclose((x * G).sum(1), f1 - f0, atol=2e-3), ((x * G).sum(1) - (f1 - f0)).abs().max()
+
+
+def test_gnn_feature_importance_layout_and_completeness():
+    """GNN attribution (torch path): frame layout of the reference (one row per class, layer and gene) and the
+    completeness axiom of Integrated Gradients on the graph encoder."""
+    from flexynesis_b200.models import attribution_path
+    from oracle.restatement import synthetic_graph
+    torch.manual_seed(0)
+    B, N, F = 10, 30, 2
+
+    class G:
+        pass
+    ds = G()
+    ds.node_features_tensor = torch.randn(B, N, F)
+    ds.edge_index = synthetic_graph(N, 70, 0)
+    ds.variable_types = {"y": "numerical"}
+    ds.ann = {"y": torch.randn(B)}
+    ds.samples = [f"s{i}" for i in range(B)]
+    ds.common_features = [f"g{i}" for i in range(N)]
+    ds.multiomic_dataset = G()
+    ds.multiomic_dataset.dat = {"rna": None, "cnv": None}
+    ds.multiomic_dataset.variable_types, ds.multiomic_dataset.ann = ds.variable_types, ds.ann
+    G.__len__ = lambda self: B
+    G.__getitem__ = lambda self, i: (self.node_features_tensor[i], {"y": self.ann["y"][i]}, self.samples[i])
+    cfg = {"latent_dim": 6, "supervisor_hidden_dim": 4, "lr": 1e-3, "node_embedding_dim": 8, "num_convs": 2,
+           "activation": "tanh"}
+    m = fx.GNN(cfg, ds, ["y"], device_type="cpu", gnn_conv_type="GC")
+    m.eval()
+    df = m.compute_feature_importance(ds, "y", steps_or_samples=6, batch_size=4)
+    assert list(df.columns) == ["target_variable", "target_class", "target_class_label", "layer", "name", "importance"]
+    assert len(df) == 2 * N and list(df.layer.unique()) == ["rna", "cnv"] and list(df.name[:3]) == ["g0", "g1", "g2"]
+    x = ds.node_features_tensor
+    alphas, weights = attribution_path("IntegratedGradients", 48)
+    Gr = torch.zeros_like(x)
+    for al, w in zip(alphas, weights):
+        xk = (x * float(al)).requires_grad_(True)
+        Gr += float(w) * torch.autograd.grad(m.forward(xk)["y"][:, 0].sum(), [xk])[0]
+    with torch.no_grad():
+        f1, f0 = m.forward(x)["y"][:, 0], m.forward(torch.zeros_like(x))["y"][:, 0]
+    assert torch.allclose((x * Gr).sum((1, 2)), f1 - f0, atol=2e-3)
