@@ -47,6 +47,10 @@ def scenarios():
         "triplet": dict(B=48, spec=Spec(
             model="MultiTripletNetwork", input_dims=[40, 24], latent_dim=16, hidden_dim_factor=0.4,
             supervisor_hidden_dim=8, variables=["c", "y"], variable_types=vt, num_classes={"c": 4})),
+        "crossmodal": dict(B=48, spec=Spec(
+            model="CrossModalPred", input_dims=[40, 24, 18], latent_dim=8, hidden_dim_factor=0.4,
+            supervisor_hidden_dim=8, variables=["c", "y"], variable_types=vt, num_classes={"c": 3},
+            in_idx=[0, 2], out_idx=[1, 2])),
         "gnn": dict(B=16, spec=Spec(
             model="GNN", input_dims=[2], latent_dim=12, supervisor_hidden_dim=8, variables=["y", "c"],
             variable_types=vt, num_classes={"c": 3}, node_count=30, node_embedding_dim=6, num_convs=2,
@@ -70,6 +74,11 @@ def build_reference(ref, spec: Spec, dat, y, edge_index=None):
         ds = ref_shim.RefGraphDataset(dat, ann_ctor, spec.variable_types, edge_index)
         return ref.gnn_early.GNN(dataset=ds, gnn_conv_type="GCN", **kw)
     ds = ref_shim.RefDataset(dat, ann_ctor, spec.variable_types)
+    if spec.model == "CrossModalPred":
+        keys = list(dat.keys())
+        return ref.crossmodal_pred.CrossModalPred(
+            dataset=ds, input_layers=[keys[i] for i in spec.in_idx] if spec.in_idx is not None else None,
+            output_layers=[keys[i] for i in spec.out_idx] if spec.out_idx is not None else None, **kw)
     cls = {"DirectPred": lambda: ref.direct_pred.DirectPred,
            "supervised_vae": lambda: ref.supervised_vae.supervised_vae,
            "MultiTripletNetwork": lambda: ref.triplet_encoder.MultiTripletNetwork}[spec.model]()
@@ -94,7 +103,7 @@ def make_batch(spec: Spec, B: int, seed: int):
 def eval_forward(model, spec, batch):
     """Eval-mode head outputs of the reference model (None for supervised_vae: its forward samples epsilon even
     in eval mode, supervised_vae.py:419-421)."""
-    if spec.model == "supervised_vae":
+    if spec.model in ("supervised_vae", "CrossModalPred"):
         return None
     model.eval()
     with torch.no_grad():
@@ -130,7 +139,7 @@ def run_reference(name: str, sc) -> dict:
                 def fwd(*a, _o=orig, **k):
                     r = _o(*a, **k); captured["emb"], captured["outputs"] = r[0], r[3]; return r
                 model.forward = fwd
-            elif spec.model == "supervised_vae":
+            elif spec.model in ("supervised_vae", "CrossModalPred"):
                 orig = model.forward
                 def fwd(*a, _o=orig, **k):
                     r = _o(*a, **k); captured["emb"], captured["outputs"] = r[1], r[4]; return r
@@ -248,7 +257,10 @@ def main():
         return 1
     os.makedirs(OUT_DIR, exist_ok=True)
     torch.set_num_threads(1)           # bit-stable sums
+    only = set(sys.argv[1:])            # optional: regenerate just the named scenarios
     for name, sc in scenarios().items():
+        if only and name not in only:
+            continue
         g = run_reference(name, sc)
         worst = check_oracle(g)
         path = os.path.join(OUT_DIR, name + ".pt")

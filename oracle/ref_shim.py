@@ -68,7 +68,7 @@ _loaded = {}
 
 def load():
     """Returns a namespace with the reference's modules: .modules, .direct_pred, .supervised_vae,
-    .triplet_encoder, .gnn_early."""
+    .triplet_encoder, .gnn_early, .crossmodal_pred."""
     if _loaded:
         return types.SimpleNamespace(**_loaded)
     if not available():
@@ -102,7 +102,7 @@ def load():
     models.__path__ = [os.path.join(REFERENCE_ROOT, "flexynesis", "models")]
     _loaded["modules"] = importlib.import_module("flexynesis.modules")
     _loaded["data"] = importlib.import_module("flexynesis.data")    # dataset containers only (data.py:945-1304)
-    for name in ("direct_pred", "supervised_vae", "triplet_encoder", "gnn_early"):
+    for name in ("direct_pred", "supervised_vae", "triplet_encoder", "gnn_early", "crossmodal_pred"):
         _loaded[name] = importlib.import_module("flexynesis.models." + name)
     return types.SimpleNamespace(**_loaded)
 

@@ -212,7 +212,7 @@ def compare_step(rep, model, spec, batch, cb, st, s, P_before_cpu, lr):
 
 
 GOLDEN = [p for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
-          if os.path.basename(p).startswith(("directpred", "triplet", "supervised_vae", "gnn"))]
+          if os.path.basename(p).startswith(("directpred", "triplet", "supervised_vae", "gnn", "crossmodal"))]
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
