@@ -139,7 +139,15 @@ def fit(model, dataset, batch_size: int, epochs: int, device="cuda", val_dataset
         loader.full_batch = False
     else:
         loader = DeviceBatcher(dataset, batch_size, device, shuffle=True, drop_last=True, seed=seed)
-    val = DeviceBatcher(val_dataset, len(val_dataset), device, shuffle=False, drop_last=False) if val_dataset else None
+    if val_dataset is None:
+        val = None
+    elif getattr(model, "main_var", None) is not None:     # triplet batches for the validation objective as well
+        vbase = getattr(val_dataset, "dataset", val_dataset)
+        nval = int((~torch.isnan(torch.as_tensor(vbase.ann[model.main_var]).float())).sum())
+        val = DeviceTripletBatcher(val_dataset, model.main_var, max(nval, 1), device, shuffle=False, drop_last=False,
+                                   seed=seed + 1)
+    else:
+        val = DeviceBatcher(val_dataset, len(val_dataset), device, shuffle=False, drop_last=False)
     history = []
     graphed = None
     for epoch in range(epochs):
