@@ -525,3 +525,39 @@ def test_device_triplet_batcher_follows_the_reference_sampling_law():
     _, q = bt.sample_indices(torch.full((4000,), int(torch.nonzero(lab == 0)[0]), device="cuda"))
     lq = labc[q]
     assert bool(torch.isnan(lq).any()) and set(lq[~torch.isnan(lq)].unique().tolist()) == {1.0, 2.0, 3.0, 9.0}
+
+
+def test_fit_loop_trains_directpred_and_triplet_with_validation():
+    """flexynesis_b200.fit.fit (the Lightning-policy loop, main.py:212-225 / :289-318): mini-batches from the device
+    batchers (plain and triplet), CUDA-graphed or eager steps, per-epoch validation; the training loss must go down."""
+    import numpy as np
+    import flexynesis_b200 as fx
+    vt = {"y": "numerical", "c": "categorical"}
+    tr = fx.SyntheticMultiOmicDataset([120, 60], 512, vt, {"c": 3}, seed=0)
+    va = fx.SyntheticMultiOmicDataset([120, 60], 128, vt, {"c": 3}, seed=1)
+    # make the labels learnable: class = argmax of three input features, y = a linear read-out
+    for ds in (tr, va):
+        x = ds.dat["layer0"]
+        ds.ann["c"] = x[:, :3].argmax(1).float()
+        ds.ann["y"] = x[:, 3] - 0.5 * x[:, 4]
+    cfg = {"latent_dim": 16, "hidden_dim_factor": 0.25, "supervisor_hidden_dim": 8, "lr": 5e-3}
+
+    class V:
+        pass
+
+    def view(ds):
+        v = V()
+        v.dat, v.features, v.variable_types, v.ann, v.samples = ds.dat, ds.features, ds.variable_types, ds.clean_ann(), ds.samples
+        return v
+    torch.manual_seed(0)
+    m = fx.DirectPred(cfg, view(tr), ["c", "y"], device_type="gpu")
+    hist = fx.fit.fit(m, tr, batch_size=128, epochs=6, val_dataset=va)
+    assert len(hist) == 6 and all(np.isfinite(h["train_loss"]) and np.isfinite(h["val_loss"]) for h in hist)
+    assert min(h["train_loss"] for h in hist[-2:]) < hist[0]["train_loss"]
+    hist_full = fx.fit.fit(fx.DirectPred(cfg, view(tr), ["c", "y"], device_type="gpu"), tr, batch_size=512, epochs=10)
+    assert min(h["train_loss"] for h in hist_full[-3:]) < hist_full[0]["train_loss"]   # full batch: the CUDA-graphed path
+    torch.manual_seed(0)
+    t = fx.MultiTripletNetwork(cfg, view(tr), ["c", "y"], device_type="gpu")
+    hist_t = fx.fit.fit(t, tr, batch_size=128, epochs=5, val_dataset=va)
+    assert all(np.isfinite(h["train_loss"]) and np.isfinite(h["val_loss"]) for h in hist_t)
+    assert min(h["train_loss"] for h in hist_t[-2:]) < hist_t[0]["train_loss"]
