@@ -85,7 +85,7 @@ lib = _load()
 # every exported symbol that include/flexynesis_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "fxn_version", "fxn_last_error", "fxn_launch_count", "fxn_reset_launch_count", "fxn_split_planes", "fxn_gemm",
-    "fxn_gemm_stat_tiles", "fxn_bn_act_fwd", "fxn_bn_act_bwd", "fxn_col_stats", "fxn_head_out_fwd", "fxn_head_out_bwd",
+    "fxn_gemm_stat_tiles", "fxn_gemm_plan", "fxn_bn_act_fwd", "fxn_bn_act_bwd", "fxn_col_stats", "fxn_head_out_fwd", "fxn_head_out_bwd",
     "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
     "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn", "fxn_gcn_fwd", "fxn_gcn_bwd",
@@ -197,6 +197,15 @@ def gemm(M, N, K, a: Planes, a_mn, b: Planes, b_mn, *, C_ptr=None, ldc=0, bias=N
     d.stats_alpha, d.stats_alpha_dev = stats_alpha, stats_alpha_dev
     d.outputs_prezeroed = int(prezeroed)
     check(lib.fxn_gemm(C.byref(d), C.c_void_p(stream())), "fxn_gemm")
+
+
+def gemm_plan(M, N, K, nterms=3, b_mn=0, plain_c=False, block_n=0) -> dict:
+    """The launch plan fxn_gemm would choose (host-side cost model; callable without a GPU)."""
+    out = (C.c_int * 8)()
+    check(lib.fxn_gemm_plan(C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(nterms), C.c_int(int(b_mn)), C.c_int(int(plain_c)),
+                            C.c_int(block_n), out), "fxn_gemm_plan")
+    keys = ("cta_group", "block_n", "stages", "streamk", "groups", "tiles_m", "tiles_n", "smem_bytes")
+    return dict(zip(keys, (int(v) for v in out)))
 
 
 def stat_tiles(M: int) -> int:

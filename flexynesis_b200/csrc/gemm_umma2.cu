@@ -789,6 +789,20 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
 }  // namespace fxn
 
 // Debug: clock64 stamps of CTA 0 and CTA 1 of the last traced launch (FXN_GEMM_TRACE=1), relative to each CTA's start.
+// Host-side planner exposed for tests and tooling (no device needed): the plan fxn_gemm would use for a problem.
+// out[0..7] = {cta_group, block_n, stages, streamk, groups (CTA pairs / CTAs), tiles_m, tiles_n, dynamic smem bytes}.
+extern "C" int fxn_gemm_plan(int M, int N, int K, int nterms, int b_mn_major, int plain_c, int block_n, int* out8) {
+  if (!out8 || M <= 0 || N <= 0 || K <= 0 || (nterms != 1 && nterms != 3))
+    return fxn::set_error(FXN_ERR_ARG, "fxn_gemm_plan: bad argument");
+  const Plan pl = make_plan(M, N, K, nterms, b_mn_major ? 1 : 0, plain_c != 0, block_n);
+  if (pl.stages < 1) return fxn::set_error(FXN_ERR_ARG, "fxn_gemm_plan: tile does not fit in shared memory");
+  const int nplanes = nterms == 3 ? 2 : 1;
+  const int stage_bytes = nplanes * (G2_BM * G2_BK * 2 + (pl.bn / pl.cg) * G2_BK * 2);
+  out8[0] = pl.cg; out8[1] = pl.bn; out8[2] = pl.stages; out8[3] = pl.streamk; out8[4] = pl.groups;
+  out8[5] = pl.tiles_m; out8[6] = pl.tiles_n; out8[7] = pl.stages * stage_bytes + G2_STG_BYTES + 1024;
+  return 0;
+}
+
 // Debug: %globaltimer (ns) at start and end of CTA i of the last traced launch, relative to the earliest start
 // (-1 = CTA index not launched).
 extern "C" int fxn_debug_gemm_cta_times(long long* start_ns, long long* end_ns, int n) {

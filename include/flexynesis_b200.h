@@ -94,6 +94,10 @@ int fxn_debug_gemm_trace(long long* out32);
  * last traced launch -- shows scheduling waves and stragglers. */
 int fxn_debug_gemm_cta_times(long long* start_ns, long long* end_ns, int n);
 int fxn_gemm_stat_tiles(int M);
+/* The launch plan fxn_gemm would choose (host-side cost model, no device needed): out8 = {cta_group, block_n, stages,
+ * streamk, groups, tiles_m, tiles_n, dynamic shared memory bytes}. plain_c != 0: the output is a plain fp32 C (stream-K
+ * eligible); block_n > 0 forces the tile width as fxn_gemm_desc.block_n does. */
+int fxn_gemm_plan(int M, int N, int K, int nterms, int b_mn_major, int plain_c, int block_n, int* out8);
 
 /* ---- BatchNorm1d (+ activation + dropout) ----
  * Forward of  y = dropout(act(BN(V)))  over the rows of V [rows x cols].

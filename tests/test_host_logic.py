@@ -131,3 +131,32 @@ def test_gnn_feature_importance_layout_and_completeness():
     with torch.no_grad():
         f1, f0 = m.forward(x)["y"][:, 0], m.forward(torch.zeros_like(x))["y"][:, 0]
     assert torch.allclose((x * Gr).sum((1, 2)), f1 - f0, atol=2e-3)
+
+
+def test_gemm_planner_invariants():
+    """fxn_gemm_plan (the C library's host-side cost model, callable without a device): for the shapes of the five
+    BASELINE configs and a sweep of ragged ones the plan must be launchable -- shared memory within the 227 KB opt-in
+    limit, all CTA groups co-resident (74 pairs / 148 CTAs), tile width a legal UMMA N for the operand layout, the tiles
+    covering N without an empty last tile, stream-K only for plain fp32 outputs, forced widths honoured."""
+    from flexynesis_b200 import _lib as L
+    shapes = [(4096, 512, 5000), (4096, 307, 3000), (4096, 256, 512), (4096, 32, 256), (512, 5000, 4096), (307, 3000, 4096),
+              (4096, 1024, 24000), (1024, 24000, 4096), (4096, 5000, 512), (4096, 4096, 128), (200, 4096, 128),
+              (512, 128, 1000), (128, 64, 128), (4096, 128, 64000), (128, 64000, 4096), (333, 307, 96), (1, 8, 8), (77, 5, 5000)]
+    for (M, N, K) in shapes:
+        for b_mn in (0, 1):
+            for plain in (False, True):
+                p = L.gemm_plan(M, N, K, 3, b_mn, plain, 0)
+                cg, bn = p["cta_group"], p["block_n"]
+                assert cg == (2 if M > 128 else 1)
+                assert p["smem_bytes"] <= 227 * 1024, (M, N, K, p)
+                assert 1 <= p["groups"] <= 148 // cg, (M, N, K, p)
+                assert bn % ((64 if b_mn else 16) * cg) == 0 and 16 <= bn <= 256, (M, N, K, p)
+                assert p["tiles_n"] * bn >= N and (p["tiles_n"] - 1) * bn < N, (M, N, K, p)
+                assert p["tiles_m"] * 128 * cg >= M and (p["tiles_m"] - 1) * 128 * cg < M
+                assert p["stages"] >= 2
+                if not plain:
+                    assert p["streamk"] == 0
+    assert L.gemm_plan(4096, 512, 5000, 3, 0, False, 256)["block_n"] == 256
+    assert L.gemm_plan(4096, 307, 3000, 3, 0, False, 160)["block_n"] == 160
+    big = L.gemm_plan(512, 5000, 4096, 3, 1, True, 0)                 # config-2 weight gradient: stream-K over every SM
+    assert big["streamk"] == 1 and big["groups"] == 74 and big["block_n"] == 256
