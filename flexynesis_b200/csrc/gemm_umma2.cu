@@ -25,7 +25,6 @@
 
 namespace fxn {
 
-constexpr int G2_THREADS = 192;
 constexpr int G2_BM = 128;          // rows of A per CTA
 constexpr int G2_BK = 64;           // one 128-byte swizzle atom of bf16 along K
 constexpr int G2_UK = 16;
@@ -303,8 +302,11 @@ __device__ __forceinline__ void epi_rows(const Gemm2Args& p, const EpiRowCtx& cx
   }
 }
 
-template <int CG>
-__global__ void __launch_bounds__(G2_THREADS, 1)
+// EW = number of epilogue warps: 4 (one per TMEM lane quarter) or 8 (two per quarter, alternating 32-column chunks: two
+// warps per scheduler hide each other's instruction latency; used for short-K, epilogue-bound problems where the second
+// set of staging buffers does not cost a pipeline stage that matters).
+template <int CG, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const Gemm2Args p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -313,7 +315,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_stat[4][2][G2_CHUNK];     // cross-warp merge of column statistics
+  __shared__ float s_stat_all[EW / 4][4][2][G2_CHUNK];     // cross-warp merge of column statistics (per chunk parity)
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
@@ -334,7 +336,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     tma_prefetch_desc(&tmB_hi);
     if (nplanes == 2) { tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_lo); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4 * CG); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EW * CG); }
     fence_mbar_init();
   }
   if (warp == 1) g2_tmem_alloc<CG>(&tmem_base_slot, p.tmem_cols);
@@ -434,6 +436,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   } else {
     // ===================== Epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;                          // 0 (EW = 4); EW = 8: which chunk parity this warp takes
+    constexpr int CH_STEP = EW / 4;
+    float (*s_stat)[2][G2_CHUNK] = s_stat_all[half];
     const uint32_t stg_s = smem_u32(stg_all + (warp - 2) * (32 * G2_STG_LD));
     const int rr = lane >> 4, cp = lane & 15;                 // transposed layout: 2 rows x 16 column pairs per pass
     const float alpha = p.alpha * (p.alpha_dev ? __ldg(p.alpha_dev) : 1.f);
@@ -457,7 +462,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       float sq_acc = 0.f;
       const int ncols_tile = min(p.bn, p.N - n0);                        // valid columns of this tile (may be <= 0 never)
       const int nchunks = (min(p.bn, padN - n0) + G2_CHUNK - 1) / G2_CHUNK;
-      for (int ch = 0; ch < nchunks; ++ch) {
+      if (half >= nchunks) {
+        // this warp has no chunk in this tile: release its share of the accumulator right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+      }
+      for (int ch = half; ch < nchunks; ch += CH_STEP) {
         const int c0 = ch * G2_CHUNK;
         uint32_t v[32];
         const uint32_t taddr = tmem_base + as * static_cast<uint32_t>(p.bn) + (static_cast<uint32_t>(q * 32) << 16) +
@@ -470,8 +481,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           for (int j = 16; j < 32; ++j) v[j] = 0;
         }
         tmem_ld_wait();
-        if (ch == nchunks - 1) {
-          // every accumulator value of this tile is in registers: hand the TMEM stage back to the MMA issuer
+        if (ch + CH_STEP >= nchunks) {
+          // every accumulator value this warp needs is in registers: hand its share of the TMEM stage back to the MMA issuer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
@@ -543,7 +554,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
               s_stat[q][0][2 * cp] = s0; s_stat[q][0][2 * cp + 1] = s1;
               s_stat[q][1][2 * cp] = m20; s_stat[q][1][2 * cp + 1] = m21;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
             if (q == 0 && lane < 32) {
               const int c = n0 + c0 + lane;
               const int tile_row0 = (sg.mt * CG + static_cast<int>(rank)) * G2_BM;
@@ -568,7 +579,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
                 dst[p.N] = tm2;
               }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
           }
         }
         __syncwarp();
@@ -660,18 +671,18 @@ Plan make_plan(int M, int N, int K, int nterms, int b_mn, bool plain_c, int forc
   return best;
 }
 
-template <int CG>
+template <int CG, int EW>
 cudaError_t launch_gemm2(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
                          const CUtensorMap& tb_lo, const Gemm2Args& p, int groups, int smem_bytes, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_MAX_DYN_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<CG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_MAX_DYN_SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * CG, 1, 1);
-  cfg.blockDim = dim3(G2_THREADS, 1, 1);
+  cfg.blockDim = dim3(64 + 32 * EW, 1, 1);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -683,11 +694,11 @@ cudaError_t launch_gemm2(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, con
   cfg.numAttrs = 1;
   if (p.trace) {
     int nclusters = -1;
-    cudaOccupancyMaxActiveClusters(&nclusters, gemm2_kernel<CG>, &cfg);
+    cudaOccupancyMaxActiveClusters(&nclusters, gemm2_kernel<CG, EW>, &cfg);
     fprintf(stderr, "[gemm2] max co-resident clusters of %d CTAs at %d B smem: %d (launching %d)\n", CG, smem_bytes, nclusters,
             groups);
   }
-  return cudaLaunchKernelEx(&cfg, gemm2_kernel<CG>, ta_hi, ta_lo, tb_hi, tb_lo, p);
+  return cudaLaunchKernelEx(&cfg, gemm2_kernel<CG, EW>, ta_hi, ta_lo, tb_hi, tb_lo, p);
 }
 
 }  // namespace
@@ -778,9 +789,24 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
   }
   const int nplanes = d->nterms == 3 ? 2 : 1;
   const int stage_bytes = nplanes * (G2_BM * G2_BK * 2 + (p.bn / pl.cg) * G2_BK * 2);
-  const int smem_bytes = p.stages * stage_bytes + G2_STG_BYTES + 1024;
-  cudaError_t e = pl.cg == 2 ? launch_gemm2<2>(ta_hi, ta_lo, tb_hi, tb_lo, p, pl.groups, smem_bytes, stream)
-                             : launch_gemm2<1>(ta_hi, ta_lo, tb_hi, tb_lo, p, pl.groups, smem_bytes, stream);
+  // Epilogue width. FXN_GEMM_EPI_WARPS=8 (opt-in; default 4) gives short-K, epilogue-bound tile-mode problems eight
+  // epilogue warps, provided the second set of staging buffers still leaves as many stages as there are k-blocks to
+  // prefetch (or at least 3).
+  static const int epi_env = [] { const char* e = getenv("FXN_GEMM_EPI_WARPS"); return e ? atoi(e) : 4; }();
+  int ew = 4;
+  if (epi_env == 8 && !p.streamk && p.kb_total <= 16) {
+    int st8 = (G2_MAX_DYN_SMEM - 1024 - 2 * G2_STG_BYTES) / stage_bytes;
+    if (st8 > p.stages) st8 = p.stages;
+    if (st8 >= 3 || (st8 >= 2 && st8 >= p.kb_total)) { ew = 8; p.stages = st8; }
+  }
+  const int smem_bytes = p.stages * stage_bytes + (ew / 4) * G2_STG_BYTES + 1024;
+  cudaError_t e;
+  if (ew == 8)
+    e = pl.cg == 2 ? launch_gemm2<2, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, pl.groups, smem_bytes, stream)
+                   : launch_gemm2<1, 8>(ta_hi, ta_lo, tb_hi, tb_lo, p, pl.groups, smem_bytes, stream);
+  else
+    e = pl.cg == 2 ? launch_gemm2<2, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, pl.groups, smem_bytes, stream)
+                   : launch_gemm2<1, 4>(ta_hi, ta_lo, tb_hi, tb_lo, p, pl.groups, smem_bytes, stream);
   if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "gemm2 launch: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
