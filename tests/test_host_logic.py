@@ -160,3 +160,43 @@ def test_gemm_planner_invariants():
     assert L.gemm_plan(4096, 307, 3000, 3, 0, False, 160)["block_n"] == 160
     big = L.gemm_plan(512, 5000, 4096, 3, 1, True, 0)                 # config-2 weight gradient: stream-K over every SM
     assert big["streamk"] == 1 and big["groups"] == 74 and big["block_n"] == 256
+
+
+def _golden(name):
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", name + ".pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("name", ["directpred_single", "directpred_fusion", "directpred_noweight", "triplet", "gnn"])
+def test_cpu_resident_inference_matches_reference_eval_outputs(name):
+    """Contract safety ("device moves"): with parameters and inputs on the CPU the drop-in classes run
+    the torch formulation of their containers; in eval mode it must reproduce what the REFERENCE produced for the same
+    state_dict (tests/golden/*.pt: `eval_outputs0`, recorded from the reference's own source)."""
+    from oracle.restatement import Spec
+    from test_gpu_parity import _DS, _GDS
+    g = _golden(name)
+    spec = Spec(**g["spec"])
+    cfg = {"latent_dim": spec.latent_dim, "hidden_dim_factor": spec.hidden_dim_factor,
+           "supervisor_hidden_dim": spec.supervisor_hidden_dim, "lr": g["lr"], "node_embedding_dim": spec.node_embedding_dim,
+           "num_convs": spec.num_convs, "activation": spec.activation}
+    targets = [v for v in spec.variables if v != spec.surv_event_var]
+    kw = dict(surv_event_var=spec.surv_event_var, surv_time_var=spec.surv_time_var,
+              use_loss_weighting=spec.use_loss_weighting, device_type="cpu")
+    batch = g["batch"]
+    if spec.model == "GNN":
+        m = fx.GNN(cfg, _GDS(batch[0], batch[1], spec.variable_types, g["edge_index"]), targets, gnn_conv_type="GCN", **kw)
+    elif spec.model == "MultiTripletNetwork":
+        m = fx.MultiTripletNetwork(cfg, _DS(batch[0], batch[3], spec.variable_types), targets, **kw)
+    else:
+        m = fx.DirectPred(cfg, _DS(batch[0], batch[1], spec.variable_types), targets, **kw)
+    m.load_state_dict(g["P0"], strict=True)
+    m.eval()
+    with torch.no_grad():
+        if spec.model == "GNN":
+            out = m.forward(batch[0])
+        elif spec.model == "MultiTripletNetwork":
+            out = m.forward(batch[0], batch[1], batch[2])[3]
+        else:
+            out = m.forward(list(batch[0].values()))
+    assert g["eval_outputs0"] is not None
+    for k, v in g["eval_outputs0"].items():
+        assert torch.allclose(out[k], v, rtol=1e-5, atol=1e-6), (name, k, float((out[k] - v).abs().max()))
