@@ -18,6 +18,9 @@ class _DS:
         self.features = {k: [f"f{j}" for j in range(v.shape[1])] for k, v in self.dat.items()}
         self.samples = [f"s{i}" for i in range(12)]
 
+    def __len__(self):
+        return len(self.samples)
+
 
 @pytest.mark.parametrize("cls", ["DirectPred", "supervised_vae", "CrossModalPred"])
 def test_state_dict_round_trips_through_safetensors(tmp_path, cls):
@@ -200,3 +203,23 @@ def test_cpu_resident_inference_matches_reference_eval_outputs(name):
     assert g["eval_outputs0"] is not None
     for k, v in g["eval_outputs0"].items():
         assert torch.allclose(out[k], v, rtol=1e-5, atol=1e-6), (name, k, float((out[k] - v).abs().max()))
+
+
+def test_predict_and_transform_formats_on_cpu():
+    """predict -> {var: ndarray} with softmax rows for categorical variables; transform -> DataFrame [samples x E0..]
+    indexed by sample name (direct_pred.py:296-415), here through the CPU-resident torch path of the drop-in classes."""
+    import numpy as np
+    torch.manual_seed(0)
+    ann = {"y": torch.randn(12), "c": torch.tensor([0., 1, 2] * 4)}
+    ds = _DS([40, 30], ann, {"y": "numerical", "c": "categorical"})
+    cfg = {"latent_dim": 8, "hidden_dim_factor": 0.25, "supervisor_hidden_dim": 4, "lr": 1e-3}
+    for cls in ("DirectPred", "supervised_vae", "CrossModalPred"):
+        m = getattr(fx, cls)(cfg, ds, ["y", "c"], device_type="cpu")
+        pred = m.predict(ds)
+        assert set(pred) == {"y", "c"} and pred["y"].shape == (12, 1) and pred["c"].shape == (12, 3)
+        assert np.allclose(pred["c"].sum(1), 1.0, atol=1e-5) and (pred["c"] >= 0).all()
+        emb = m.transform(ds)
+        assert list(emb.index) == ds.samples and list(emb.columns) == [f"E{i}" for i in range(8)]
+        assert np.isfinite(emb.to_numpy()).all()
+    dec = fx.CrossModalPred(cfg, ds, ["y"], input_layers=["l0"], output_layers=["l1"], device_type="cpu").decode(ds)
+    assert set(dec) == {"l1"} and dec["l1"].shape == (30, 12) and list(dec["l1"].columns) == ds.samples
