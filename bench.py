@@ -324,14 +324,14 @@ def roofline_gemm(model, w, dev):
         out, bias, epi = ws["Z"][0], eng.arena.p("encoders.0.layer_1.bias"), 0
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
-    def timed(block_n):
+    def timed(block_n, groups=0):
         evs = []
         for _ in range(13):
             flush.zero_()                               # > L2: the next launch reads its operands from HBM
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             L.gemm(M, N, K, ws["X"][0], 0, eng.wp(eng.w1[0]), 0, C_ptr=out.data_ptr(), ldc=out.stride(0), bias=bias,
-                   epi_act=epi, colstats=ws["partials"][0].data_ptr(), stats_mode=2, block_n=block_n)
+                   epi_act=epi, colstats=ws["partials"][0].data_ptr(), stats_mode=2, block_n=block_n, max_groups=groups)
             a1.record()
             evs.append((a0, a1))
         torch.cuda.synchronize()
@@ -339,15 +339,17 @@ def roofline_gemm(model, w, dev):
         return sum(durs) / len(durs)
 
     avg_ms = timed(0)                                   # the library's own plan for a kernel that has the chip to itself
-    # inside the step the first-layer GEMMs of all modalities run as parallel graph branches on disjoint SMs with wider,
-    # MMA-paced tiles (engine.concurrent_tile_widths): the same kernel in that shape, for the record
-    from flexynesis_b200.engine import concurrent_tile_widths
-    step_bn = concurrent_tile_widths(B, eng.h, eng.d)[0] if hasattr(eng, "h") and len(eng.h) > 1 else 0
+    # inside the step the first-layer GEMMs of all modalities run as parallel graph branches, each on its share of the SM
+    # pairs (engine.concurrent_plan): the same kernel in that shape, for the record
+    from flexynesis_b200.engine import concurrent_plan
+    step_bn, step_groups = concurrent_plan(B, eng.h, eng.d)[0] if hasattr(eng, "h") and len(eng.h) > 1 else (0, 0)
     in_step = None
     if step_bn:
-        ms2 = timed(step_bn)
-        in_step = {"block_n": step_bn, "avg_launch_us": ms2 * 1e3, "achieved": 2.0 * M * N * K / (ms2 * 1e-3) / 1e12,
-                   "note": "this launch shape occupies 64 of 148 SMs by design; the other SMs run the second modality's GEMM"}
+        ms2 = timed(step_bn, step_groups)
+        in_step = {"block_n": step_bn, "groups": step_groups, "avg_launch_us": ms2 * 1e3,
+                   "achieved": 2.0 * M * N * K / (ms2 * 1e-3) / 1e12,
+                   "note": f"this launch shape occupies {2 * step_groups} of 148 SMs by design; the other SMs run the other "
+                           "modalities' GEMMs"}
     try:
         ev = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(w.get("name", ""), {})
     except Exception:

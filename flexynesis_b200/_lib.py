@@ -34,6 +34,9 @@ class GemmDesc(C.Structure):
         ("gauss_ra", C.c_void_p), ("gauss_rb", C.c_void_p), ("gauss_inv", C.c_float),
         ("stats_alpha", C.c_float), ("stats_alpha_dev", C.c_void_p),
         ("outputs_prezeroed", C.c_int),
+        ("max_groups", C.c_int),
+        ("fix_ws", C.c_void_p), ("fix_ws_bytes", c_ll),
+        ("fix_flags", C.c_void_p), ("fix_flags_count", c_ll),
     ]
 
 
@@ -77,6 +80,7 @@ def _load():
     lib.fxn_last_error.restype = C.c_char_p
     lib.fxn_launch_count.restype = c_ll
     lib.fxn_version.restype = C.c_int
+    lib.fxn_gemm_fix_ws_bytes.restype = c_ll
     return lib
 
 
@@ -85,7 +89,7 @@ lib = _load()
 # every exported symbol that include/flexynesis_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "fxn_version", "fxn_last_error", "fxn_launch_count", "fxn_reset_launch_count", "fxn_split_planes", "fxn_gemm",
-    "fxn_gemm_stat_tiles", "fxn_gemm_plan", "fxn_bn_act_fwd", "fxn_bn_act_bwd", "fxn_col_stats", "fxn_head_out_fwd", "fxn_head_out_bwd",
+    "fxn_gemm_stat_tiles", "fxn_gemm_plan", "fxn_gemm_fix_ws_bytes", "fxn_gemm_fix_flag_words", "fxn_bn_act_fwd", "fxn_bn_act_bwd", "fxn_col_stats", "fxn_head_out_fwd", "fxn_head_out_bwd",
     "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
     "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn", "fxn_gcn_fwd", "fxn_gcn_bwd",
@@ -178,7 +182,7 @@ def split_planes(src: torch.Tensor, dst: Planes) -> None:
 def gemm(M, N, K, a: Planes, a_mn, b: Planes, b_mn, *, C_ptr=None, ldc=0, bias=None, out: Planes = None,
          colstats=None, stats_mode=0, splitk=0, nterms=3, block_n=0, epi_act=0, accumulate=False, alpha=0.0,
          alpha_dev=None, mse_x=None, ldx=0, mse_acc=None, gauss_ra=None, gauss_rb=None, gauss_inv=0.0,
-         stats_alpha=0.0, stats_alpha_dev=None, prezeroed=False) -> None:
+         stats_alpha=0.0, stats_alpha_dev=None, prezeroed=False, max_groups=0, fix: "FixWorkspace" = None) -> None:
     d = GemmDesc()
     d.M, d.N, d.K = int(M), int(N), int(K)
     d.a_hi, d.a_lo, d.lda, d.a_mn_major = a.hi_ptr, a.lo_ptr, a.ld, int(a_mn)
@@ -196,14 +200,30 @@ def gemm(M, N, K, a: Planes, a_mn, b: Planes, b_mn, *, C_ptr=None, ldc=0, bias=N
     d.gauss_ra, d.gauss_rb, d.gauss_inv = gauss_ra, gauss_rb, gauss_inv
     d.stats_alpha, d.stats_alpha_dev = stats_alpha, stats_alpha_dev
     d.outputs_prezeroed = int(prezeroed)
+    d.max_groups = int(max_groups)
+    if fix is not None:
+        d.fix_ws, d.fix_ws_bytes = fix.ws.data_ptr(), fix.ws.numel() * 4
+        d.fix_flags, d.fix_flags_count = fix.flags.data_ptr(), fix.flags.numel()
     check(lib.fxn_gemm(C.byref(d), C.c_void_p(stream())), "fxn_gemm")
 
 
-def gemm_plan(M, N, K, nterms=3, b_mn=0, plain_c=False, block_n=0) -> dict:
-    """The launch plan fxn_gemm would choose (host-side cost model; callable without a GPU)."""
+class FixWorkspace:
+    """Workspace of the GEMM's stream-K-with-fix-up mode (partial accumulators of split tiles + flags). Zeroed once; the
+    kernel hands it back zeroed. One instance per chain of launches that cannot overlap in time (one per stream / graph
+    branch)."""
+
+    def __init__(self, device):
+        self.ws = torch.zeros(int(lib.fxn_gemm_fix_ws_bytes()) // 4, dtype=torch.float32, device=device)
+        self.flags = torch.zeros(int(lib.fxn_gemm_fix_flag_words()), dtype=torch.int32, device=device)
+
+
+def gemm_plan(M, N, K, nterms=3, b_mn=0, plain_c=False, block_n=0, fix=False, max_groups=0) -> dict:
+    """The launch plan fxn_gemm would choose (host-side cost model; callable without a GPU). plain_c: plain fp32 output
+    (stream-K eligible); fix: a fix-up workspace is available (stream-K with fix-up eligible for fused epilogues)."""
     out = (C.c_int * 8)()
-    check(lib.fxn_gemm_plan(C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(nterms), C.c_int(int(b_mn)), C.c_int(int(plain_c)),
-                            C.c_int(block_n), out), "fxn_gemm_plan")
+    mode = 1 if plain_c else (2 if fix else 0)
+    check(lib.fxn_gemm_plan(C.c_int(M), C.c_int(N), C.c_int(K), C.c_int(nterms), C.c_int(int(b_mn)), C.c_int(mode),
+                            C.c_int(int(block_n) | (int(max_groups) << 16)), out), "fxn_gemm_plan")
     keys = ("cta_group", "block_n", "stages", "streamk", "groups", "tiles_m", "tiles_n", "smem_bytes")
     return dict(zip(keys, (int(v) for v in out)))
 

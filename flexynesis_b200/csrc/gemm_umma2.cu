@@ -1,7 +1,7 @@
 // gemm2: persistent tcgen05 GEMM, C[M,N] = sum over bf16 split terms of A[M,K] * B[N,K]^T, one kernel for every dense
-// contraction of the training step (same operand conventions as gemm_umma.cu, which stays as the reference path).
+// contraction of the training step.
 //
-// What changed against gemm_umma.cu and why (profiles/r01_*):
+// Design points and why (profiles/r01_*, profiles/r02_*):
 //  * CTA PAIRS (tcgen05 cta_group::2, cluster 2x1x1): a pair computes a 256 x bn tile; each CTA stages its own 128 rows
 //    of A and only HALF of the B tile, the MMA reads both halves through the pair's shared-memory window. The mid-size
 //    GEMMs of the step (M = 4096, K = 5000, N = 512) are bound by L2 -> SM operand traffic, not by the tensor pipe:
@@ -12,7 +12,13 @@
 //  * CHUNKED EPILOGUE: 32-column chunks are transposed through a 4.5 KB per-warp staging buffer instead of a full
 //    128 x bn fp32 tile, which frees the shared memory for pipeline stages.
 //  * STREAM-K for plain fp32 outputs (the wgrads, K = batch): the (tile, k-block) space is cut into equal contiguous
-//    ranges, one per CTA pair, partial tiles are combined with fp32 reductions into the zeroed C.
+//    ranges, one per CTA pair, partial tiles are combined with 16-byte vector reductions into the zeroed C.
+//  * STREAM-K WITH FIX-UP for every other epilogue (streamk = 2): the group that holds the LAST k-block of a tile owns
+//    its epilogue; groups holding earlier k-blocks store their raw partial accumulators into their own workspace slot
+//    (register order, fully coalesced, no shared-memory staging, no atomics) and raise a flag; the owner adds the slots
+//    of its contributors to its own accumulator, in a fixed order, before the fused epilogue. Each group runs its trailing (contributor)
+//    segment FIRST, so an owner never waits on work that is queued behind another owner's wait. This is what lets a
+//    32-tile problem (config 2's [4096 x 512] layer) run MMA-paced 256-wide tiles on a caller-chosen number of SMs.
 //
 // Roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA of the pair only) + TMEM
 // allocation, warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
@@ -54,6 +60,8 @@ struct Gemm2Args {
   float stats_alpha; const float* stats_alpha_dev;
   int trace;
   int epi_variant;        // index of the specialised epilogue loop for interior chunks, -1 = generic only
+  float* fix_ws;          // streamk == 2: [groups][CG][4 quarters][bn / 32][8][32 lanes][4] fp32 partial accumulators
+  unsigned* fix_flags;    // streamk == 2: [2][groups]: contributor arrivals, owner departures (zero between launches)
 };
 
 // ---- PTX pieces that differ between cta_group::1 and ::2 ----
@@ -105,6 +113,12 @@ __device__ __forceinline__ void g2_tma_load(void* smem_dst, const CUtensorMap* m
                      smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar), "r"(c0), "r"(c1) : "memory");
   }
 }
+// one lane of a converged warp (elect.sync): the issuing lane of the TMA / MMA roles
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -135,38 +149,62 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   } while (0)
 
 // ---- work decomposition shared by the three roles ----
-struct Segment { int mt, nt, kb0, kb1; };
+struct Segment { int mt, nt, kb0, kb1; long long tile; };
 struct WorkIter {
   long long u, end;     // stream-K: position / end in the (tile, k-block) space; tile mode: tile index / tile count
+  long long tail0;      // stream-K: start of the trailing partial segment, which is processed FIRST (-1: none / done)
+  long long units, tail_end;
   int step;             // tile mode: stride
-  int kb_total, tiles_n, streamk;
-  __device__ __forceinline__ WorkIter(const Gemm2Args& p, int group, int ngroups) {
-    kb_total = p.kb_total; tiles_n = p.tiles_n; streamk = p.streamk;
+  int kb_total, tiles_n, streamk, group, ngroups;
+  __device__ __forceinline__ long long bound(int g) const { return units * g / ngroups; }
+  __device__ __forceinline__ WorkIter(const Gemm2Args& p, int group_, int ngroups_) {
+    kb_total = p.kb_total; tiles_n = p.tiles_n; streamk = p.streamk; group = group_; ngroups = ngroups_;
     const long long tiles = static_cast<long long>(p.tiles_m) * p.tiles_n;
+    units = tiles * kb_total;
+    tail0 = -1; tail_end = 0;
     if (streamk) {
-      const long long units = tiles * kb_total;
-      u = units * group / ngroups;
-      end = units * (group + 1) / ngroups;
+      u = bound(group);
+      end = bound(group + 1);
       step = 0;
+      // A range that stops inside a tile ends with a CONTRIBUTOR segment (it does not hold the tile's last k-block). Run it
+      // first: the owner of that tile is the next group, and it must not have to wait until this group has worked through
+      // everything in front of the segment (or, transitively, through this group's own wait for ITS contributors).
+      const long long last_tile_start = end / kb_total * kb_total;
+      if (end != last_tile_start && last_tile_start > u) { tail0 = last_tile_start; tail_end = end; end = last_tile_start; }
     } else {
       u = group; end = tiles; step = ngroups;
     }
   }
+  __device__ __forceinline__ void fill(Segment& s, long long a, long long b) const {
+    const long long tile = a / kb_total;
+    s.tile = tile;
+    s.kb0 = static_cast<int>(a - tile * kb_total);
+    s.kb1 = static_cast<int>(b - tile * kb_total);
+    s.mt = static_cast<int>(tile / tiles_n); s.nt = static_cast<int>(tile - static_cast<long long>(s.mt) * tiles_n);
+  }
   __device__ __forceinline__ bool next(Segment& s) {
-    if (u >= end) return false;
     if (streamk) {
-      const long long tile = u / kb_total;
-      s.kb0 = static_cast<int>(u - tile * kb_total);
-      const long long room = end - u;
-      s.kb1 = static_cast<int>(room < kb_total - s.kb0 ? s.kb0 + room : kb_total);
-      s.mt = static_cast<int>(tile / tiles_n); s.nt = static_cast<int>(tile - static_cast<long long>(s.mt) * tiles_n);
-      u += s.kb1 - s.kb0;
-    } else {
-      s.mt = static_cast<int>(u / tiles_n); s.nt = static_cast<int>(u - static_cast<long long>(s.mt) * tiles_n);
-      s.kb0 = 0; s.kb1 = kb_total;
-      u += step;
+      if (tail0 >= 0) { fill(s, tail0, tail_end); tail0 = -1; return true; }
+      if (u >= end) return false;
+      const long long tile_end = (u / kb_total + 1) * kb_total;
+      const long long b = tile_end < end ? tile_end : end;
+      fill(s, u, b);
+      u = b;
+      return true;
     }
+    if (u >= end) return false;
+    s.tile = u;
+    s.mt = static_cast<int>(u / tiles_n); s.nt = static_cast<int>(u - static_cast<long long>(s.mt) * tiles_n);
+    s.kb0 = 0; s.kb1 = kb_total;
+    u += step;
     return true;
+  }
+  // group that holds unit x (largest g with bound(g) <= x)
+  __device__ __forceinline__ int group_of(long long x) const {
+    int g = static_cast<int>(x * ngroups / units);
+    while (g + 1 < ngroups && bound(g + 1) <= x) ++g;
+    while (g > 0 && bound(g) > x) --g;
+    return g;
   }
 };
 
@@ -183,6 +221,48 @@ __device__ __forceinline__ void sts_f2(uint32_t a, float2 v) {
 }
 __device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, float w) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+// 16-byte vector reduction into global memory (REDG.E.ADD.F32x4): one L2 atomic request per four accumulator values
+__device__ __forceinline__ void red_add_f4(float* p, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+__device__ __forceinline__ float4 ldcg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Stream-K partial tile -> C for an interior chunk whose rows are 16-byte aligned: lane = (row % 4, four consecutive
+// columns), 8 passes over the staged 32 x 32 chunk. The scalar form issued 32 REDs per lane and chunk and made the
+// weight-gradient epilogue as long as its main loop (profiles/r02_wgrad_red.log).
+__device__ __forceinline__ void epi_red4(const Gemm2Args& p, uint32_t stg_s, int lane, int mbase, int col0, float alpha,
+                                         bool add_bias, int rows_valid) {
+  const int r4 = lane >> 3, c4 = (lane & 7) * 4;
+  float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  if (add_bias) {
+    b0 = __ldg(p.bias + col0 + c4); b1 = __ldg(p.bias + col0 + c4 + 1);
+    b2 = __ldg(p.bias + col0 + c4 + 2); b3 = __ldg(p.bias + col0 + c4 + 3);
+  }
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = lds_f4(stg_s + ((4 * i + r4) * G2_STG_LD + c4) * 4);
+  float* cp = p.C + static_cast<long long>(mbase + r4) * p.ldc + col0 + c4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (4 * i + r4 < rows_valid)
+      red_add_f4(cp + static_cast<long long>(4 * i) * p.ldc, fmaf(v[i].x, alpha, b0), fmaf(v[i].y, alpha, b1),
+                 fmaf(v[i].z, alpha, b2), fmaf(v[i].w, alpha, b3));
 }
 
 // ---- epilogue inner loop: 16 passes over a staged 32 x 32 chunk, lane = (row parity, column pair) ----
@@ -237,7 +317,7 @@ __device__ __forceinline__ void epi_rows(const Gemm2Args& p, const EpiRowCtx& cx
 #pragma unroll (RT ? 4 : 16)
   for (int i = 0; i < 16; ++i) {
     const int r = 2 * i + cx.rr;
-    const bool rok = RT ? (r < cx.rows_valid) : true;
+    const bool rok = r < cx.rows_valid;      // specialised variants too: a ragged last row quarter (M % 32 != 0) stays on them
     const bool ok0 = RT ? cx.ok0 : true, ok1 = RT ? cx.ok1 : true;
     float2 x;
     if constexpr (RT) x = lds_f2(cx.stg + 2 * i * G2_STG_LD * 4); else x = xin[i];
@@ -318,7 +398,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   __shared__ float s_stat_all[EW / 4][4][2][G2_CHUNK];     // cross-warp merge of column statistics (per chunk parity)
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int group = blockIdx.x / CG, ngroups = gridDim.x / CG;
@@ -347,18 +427,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const uint32_t tmem_base = tmem_base_slot;
   if (threadIdx.x == 0) G2_STAMP(1);
 
+  // The two single-thread roles run with the WHOLE warp in convergent control flow and one elected lane issuing: every
+  // address / descriptor is then warp-uniform for the compiler (uniform registers feed UTMALDG / UTCHMMA directly).
+  // Written as `if (lane == 0)` the same code compiled to a per-instruction "which lane holds the operand" loop around each
+  // TMA and MMA issue, ~1060 cycles of issue work per k-block: every tile narrower than 224 columns ran at that floor
+  // instead of at its MMA time (profiles/r02_bn_sweep_before.log).
   if (warp == 0) {
-    // ===================== TMA producer (one lane, every CTA of the group) =====================
-    if (lane == 0) {
-      WorkIter it(p, group, ngroups);
-      Segment sg;
-      int stage = 0;
-      uint32_t phase = 0;
-      while (it.next(sg)) {
-        const int m0 = (sg.mt * CG + static_cast<int>(rank)) * G2_BM;
-        const int n0 = sg.nt * p.bn + static_cast<int>(rank) * bnl;
-        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================== TMA producer (every CTA of the group) =====================
+    WorkIter it(p, group, ngroups);
+    Segment sg;
+    int stage = 0;
+    uint32_t phase = 0;
+    while (it.next(sg)) {
+      const int m0 = (sg.mt * CG + static_cast<int>(rank)) * G2_BM;
+      const int n0 = sg.nt * p.bn + static_cast<int>(rank) * bnl;
+      for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_bytes * CG);
           const int k0 = kb * G2_BK;
@@ -380,18 +465,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
                 g2_tma_load<CG>(sb + a * (G2_BK * 128), tb, &full_bar[stage], n0 + a * 64, k0);
             }
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
           if (kb == sg.kb0) G2_STAMP(2);        // first load of the (last) segment issued
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      G2_STAMP(3);                              // all loads issued
     }
+    if (lane == 0) G2_STAMP(3);                 // all loads issued
   } else if (warp == 1) {
-    // ===================== MMA issuer: one thread of the leader CTA =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer: the leader CTA's warp 1, one elected lane =====================
+    if (rank == 0) {
       const uint32_t idesc = umma_idesc_bf16(G2_BM * CG, p.bn, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? G2_BK * 128 : 16, b_lbo = p.b_mn ? G2_BK * 128 : 16;
       const uint32_t a_kstep = p.a_mn ? G2_UK * 128 : G2_UK * 2, b_kstep = p.b_mn ? G2_UK * 128 : G2_UK * 2;
+      // descriptors of one stage differ from those of stage 0 / k-step 0 only in the 14-bit start-address field
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t da0 = umma_smem_desc_sw128(smem0, a_lbo, 1024);
+      const uint64_t db0 = umma_smem_desc_sw128(smem0 + nplanes * a_bytes, b_lbo, 1024);
       WorkIter it(p, group, ngroups);
       Segment sg;
       int stage = 0;
@@ -405,33 +495,37 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         uint32_t acc = 0;
         for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
-          if (kb == sg.kb0 && tile_iter == 0) G2_STAMP(4);   // first stage landed
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sa_hi = st, sa_lo = st + a_bytes;
-          const uint32_t sb_hi = st + nplanes * a_bytes, sb_lo = sb_hi + b_bytes;
+          if (elect_one()) {
+            if (kb == sg.kb0 && tile_iter == 0) G2_STAMP(4);   // first stage landed
+            const uint32_t soff = static_cast<uint32_t>(stage) * stage_bytes;
 #pragma unroll
-          for (int kk = 0; kk < G2_BK / G2_UK; ++kk) {
-            const uint64_t da_hi = umma_smem_desc_sw128(sa_hi + kk * a_kstep, a_lbo, 1024);
-            const uint64_t db_hi = umma_smem_desc_sw128(sb_hi + kk * b_kstep, b_lbo, 1024);
-            if (nplanes == 2) {
-              const uint64_t da_lo = umma_smem_desc_sw128(sa_lo + kk * a_kstep, a_lbo, 1024);
-              const uint64_t db_lo = umma_smem_desc_sw128(sb_lo + kk * b_kstep, b_lbo, 1024);
-              g2_mma<CG>(tmem_acc, da_lo, db_hi, idesc, acc);   // small terms first
+            for (int kk = 0; kk < G2_BK / G2_UK; ++kk) {
+              const uint64_t da_hi = da0 + ((soff + kk * a_kstep) >> 4);
+              const uint64_t db_hi = db0 + ((soff + kk * b_kstep) >> 4);
+              if (nplanes == 2) {
+                const uint64_t da_lo = da_hi + (a_bytes >> 4);
+                const uint64_t db_lo = db_hi + (b_bytes >> 4);
+                g2_mma<CG>(tmem_acc, da_lo, db_hi, idesc, acc);   // small terms first
+                g2_mma<CG>(tmem_acc, da_hi, db_lo, idesc, 1u);
+                g2_mma<CG>(tmem_acc, da_hi, db_hi, idesc, 1u);
+              } else {
+                g2_mma<CG>(tmem_acc, da_hi, db_hi, idesc, acc);
+              }
               acc = 1;
-              g2_mma<CG>(tmem_acc, da_hi, db_lo, idesc, acc);
             }
-            g2_mma<CG>(tmem_acc, da_hi, db_hi, idesc, acc);
-            acc = 1;
+            g2_commit<CG>(&empty_bar[stage]);                    // frees this stage in every CTA of the group
+            if (kb + 1 == sg.kb1) {
+              g2_commit<CG>(&tfull_bar[as]);                     // accumulator complete -> both epilogues
+              if (tile_iter == 0) G2_STAMP(5);                 // first tile fully issued
+            }
           }
-          g2_commit<CG>(&empty_bar[stage]);                    // frees this stage in every CTA of the group
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        g2_commit<CG>(&tfull_bar[as]);                         // accumulator complete -> both epilogues
-        if (tile_iter == 0) G2_STAMP(5);                     // first tile fully issued
         ++tile_iter;
       }
-      G2_STAMP(6);                                           // all MMAs issued
+      if (lane == 0) G2_STAMP(6);                              // all MMAs issued
     }
   } else {
     // ===================== Epilogue: 4 warps, TMEM lane quarter = warp % 4 =====================
@@ -446,6 +540,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     const int padN = (p.N + 7) & ~7;
     const bool c_vec2 = p.C && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0) && (p.ldc % 2 == 0);
     const bool x_vec2 = p.mse_x && ((reinterpret_cast<uintptr_t>(p.mse_x) & 7) == 0) && (p.ldx % 2 == 0);
+    const bool c_vec4 = p.C && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
     WorkIter it(p, group, ngroups);
     Segment sg;
     uint32_t tile_iter = 0;
@@ -454,14 +549,45 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const int mbase = (sg.mt * CG + static_cast<int>(rank)) * G2_BM + q * 32;   // first row of this warp's quarter
       const int n0 = sg.nt * p.bn;
       const int rows_valid = max(0, min(32, p.M - mbase));
-      const bool add_bias = p.bias != nullptr && sg.kb0 == 0;
-      const bool atomic_out = p.streamk != 0;
+      // stream-K with fix-up (streamk == 2): the segment holding the tile's last k-block owns the epilogue
+      const bool fix = p.streamk == 2;
+      const bool owner = sg.kb1 == p.kb_total;
+      const bool contributor = fix && !owner;
+      const bool has_contrib = fix && owner && sg.kb0 > 0;
+      const bool add_bias = p.bias != nullptr && (fix ? owner : sg.kb0 == 0);
+      // a stream-K segment that covers the whole K range of its tile is the only contributor: plain stores into the zeroed C
+      const bool whole_tile = sg.kb0 == 0 && sg.kb1 == p.kb_total;
+      const bool atomic_out = p.streamk == 1 && !whole_tile;
+      // Workspace slot g = the partial accumulator of group g's (single) contributor segment, this warp's part being
+      // [rank][quarter][chunk][8][32 lanes][4] floats in register order; flag word g counts the epilogue warps of group g
+      // whose slot stores are visible, flag word ngroups + g the owner warps of group g that are done with their slots.
+      const size_t nch_ws = static_cast<size_t>((p.bn + G2_CHUNK - 1) / G2_CHUNK);
+      const size_t slot_floats = static_cast<size_t>(CG) * 4 * nch_ws * 1024;
+      const size_t warp_off = ((static_cast<size_t>(rank) * 4 + q) * nch_ws) * 1024 + lane * 4;
+      float* my_slot = contributor ? p.fix_ws + static_cast<size_t>(group) * slot_floats + warp_off : nullptr;
+      int ncontrib = 0;
       mbar_wait(&tfull_bar[as], aphase);
       if (warp == 2 && lane == 0 && tile_iter == 0) G2_STAMP(7);   // first accumulator ready
       tc_fence_after();
+      if (has_contrib) {
+        // contributors = the groups directly in front of this one whose (non-empty) ranges reach into this tile
+        const long long tile_start = sg.tile * p.kb_total;
+        for (int g = group - 1; g >= 0 && it.bound(g + 1) > tile_start; --g) ++ncontrib;
+        if (lane == 0) {
+          const long long t0 = clock64();
+          for (int c = 1; c <= ncontrib; ++c)
+            while (ld_acquire_u32(p.fix_flags + (group - c)) < 4u * CG) {
+              if (clock64() - t0 > 4000000000LL) { printf("fxn: gemm fix-up wait timeout (block %d)\n", blockIdx.x); __trap(); }
+            }
+        }
+        __syncwarp();
+      }
       float sq_acc = 0.f;
       const int ncols_tile = min(p.bn, p.N - n0);                        // valid columns of this tile (may be <= 0 never)
-      const int nchunks = (min(p.bn, padN - n0) + G2_CHUNK - 1) / G2_CHUNK;
+      int nchunks = (min(p.bn, padN - n0) + G2_CHUNK - 1) / G2_CHUNK;
+      // a row quarter that lies entirely below the matrix (ragged M: 307 rows in 256-row pair tiles) has nothing to write;
+      // per-tile statistics keep all four warps in step (they meet at a named barrier per chunk), fix-up slots are read whole
+      if (rows_valid == 0 && p.stats_mode != 2 && !fix) nchunks = 0;
       if (half >= nchunks) {
         // this warp has no chunk in this tile: release its share of the accumulator right away
         tc_fence_before();
@@ -487,6 +613,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
         }
+        if (contributor) {
+          // raw partial accumulators -> this group's slot, in register order: one warp-level 16-byte store instruction
+          // covers 512 contiguous bytes (no shared-memory staging, no atomics: every slot has exactly one writer)
+          float* wp_ = my_slot + static_cast<size_t>(ch) * 1024;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(reinterpret_cast<float4*>(wp_ + j * 128),
+                   make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3])));
+          continue;
+        }
+        for (int c = 1; c <= ncontrib; ++c) {      // owner of a split tile: add the contributors' partials (fixed order)
+          const float* wp_ = p.fix_ws + static_cast<size_t>(group - c) * slot_floats + warp_off + static_cast<size_t>(ch) * 1024;
+          float4 pv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pv[j] = ldcg_f4(wp_ + j * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + pv[j].x);
+            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + pv[j].y);
+            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + pv[j].z);
+            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + pv[j].w);
+          }
+        }
         __syncwarp();
         // lane = row: 32 consecutive columns -> staging (row stride 36 floats)
 #pragma unroll
@@ -506,9 +656,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         cx.mbase = mbase; cx.rr = rr; cx.col = col; cx.rows_valid = rows_valid; cx.ok0 = ok0; cx.ok1 = ok1;
         cx.alpha = alpha; cx.b0 = b0; cx.b1 = b1; cx.rb0 = rb0; cx.rb1 = rb1; cx.padN = padN;
         cx.c_vec2 = c_vec2; cx.x_vec2 = x_vec2; cx.atomic_out = atomic_out;
-        const bool interior = rows_valid == 32 && n0 + c0 + G2_CHUNK <= p.N && (c_vec2 || p.C == nullptr) &&
+        // specialised loops need 32 valid, vector-aligned columns; rows may be ragged except where the loop fetches its
+        // old C / reconstruction targets up front (variants 7 and 8)
+        const bool full_rows = rows_valid == 32 || (rows_valid > 0 && p.epi_variant != 7 && p.epi_variant != 8);
+        const bool interior = full_rows && n0 + c0 + G2_CHUNK <= p.N && (c_vec2 || p.C == nullptr) &&
                               (x_vec2 || p.mse_x == nullptr);
-        switch (interior ? p.epi_variant : -1) {
+        int variant = interior ? p.epi_variant : -1;
+        if (variant == 6) variant = whole_tile ? 0 : (c_vec4 ? 12 : 6);
+        switch (variant) {
           //                         ACT CMODE PLANES STATS MSE
           case 0:  epi_rows<false, 0, 1, false, 0, false>(p, cx, s0, s1, sq_acc); break;   // plain fp32 output
           case 1:  epi_rows<false, 0, 1, false, 2, false>(p, cx, s0, s1, sq_acc); break;   // MLP layer_1 forward (+ BN partials)
@@ -522,6 +677,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           case 9:  epi_rows<false, 7, 0, true, 3, false>(p, cx, s0, s1, sq_acc); break;    // Gaussian-kernel Gram
           case 10: epi_rows<false, 0, 1, true, 3, false>(p, cx, s0, s1, sq_acc); break;    // fp32 + planes + column sums
           case 11: epi_rows<false, 6, 1, false, 0, false>(p, cx, s0, s1, sq_acc); break;   // hidden forward, eval mode
+          case 12: epi_red4(p, stg_s, lane, mbase, n0 + c0, alpha, add_bias, rows_valid); break;   // stream-K, vector reductions
           default: epi_rows<true, 0, 0, false, 0, false>(p, cx, s0, s1, sq_acc); break;    // edges / anything else
         }
         if (p.stats_mode != 0) {
@@ -584,7 +740,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         __syncwarp();
       }
-      if (p.mse_x != nullptr) {
+      if (contributor) {
+        __threadfence();                       // this lane's slot stores are visible before the flag is raised
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.fix_flags + group, 1u);
+      } else if (ncontrib > 0) {
+        __syncwarp();
+        if (lane == 0) {
+          // the last owner warp to leave resets the flags it consumed for the next launch (every owner warp of this tile is
+          // past its wait by then; a contributor group feeds exactly one owner)
+          const unsigned old = atomicAdd(p.fix_flags + ngroups + group, 1u);
+          if (old == 4u * CG - 1u) {
+            for (int c = 1; c <= ncontrib; ++c) p.fix_flags[group - c] = 0u;
+            p.fix_flags[ngroups + group] = 0u;
+          }
+        }
+      }
+      if (p.mse_x != nullptr && !contributor) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq_acc += __shfl_xor_sync(0xffffffffu, sq_acc, o);
         if (lane == 0) atomicAdd(p.mse_acc, sq_acc);
@@ -615,17 +787,26 @@ namespace {
 
 struct Plan { int cg, bn, stages, streamk, groups, tiles_m, tiles_n; };
 
-// Pick CTA-group size, tile width and scheduling mode with a small analytic cost model (SM cycles; constants from the
-// pipeline traces in profiles/r01_gemm2_trace.log). Tile mode keeps the whole K per tile (needed by every fused
-// epilogue); stream-K needs a plain fp32 C.
-Plan make_plan(int M, int N, int K, int nterms, int b_mn, bool plain_c, int force_bn) {
+// Pick CTA-group size, tile width and scheduling mode with a small analytic cost model (SM cycles). Constants from the
+// pipeline traces (profiles/r02_bn_sweep_after.log): a k-block of a pair tile costs max(MMA time = nterms * 4
+// instructions of bn / 2 cycles + ~90, operand ingest at ~58 B/clk per SM) -- 691 / 857 / 1057 / 1244 / 1604 cycles at
+// bn = 64 / 128 / 160 / 192 / 256, i.e. MMA-paced from 128 columns up; the epilogue costs ~1450 cycles per 32-column
+// chunk and only the last one of a CTA is exposed.
+//   mode 0  whole tiles (any epilogue)
+//   mode 1  stream-K, vector reductions into a zeroed plain fp32 C
+//   mode 2  stream-K with fix-up through a workspace (any epilogue; needs fxn_gemm_desc.fix_ws)
+// group_limit > 0 caps the number of CTA groups (the engine splits the SMs between GEMMs that run concurrently).
+Plan make_plan(int M, int N, int K, int nterms, int b_mn, bool plain_c, int force_bn, bool fix_ok = false, int group_limit = 0) {
   const int nplanes = nterms == 3 ? 2 : 1;
   const int kb_total = (K + G2_BK - 1) / G2_BK;
   const int cg = M > G2_BM ? 2 : 1;
   const int unit = b_mn ? 64 * cg : 16 * cg;                   // per-CTA B rows: multiple of 64 (MN-major) or 16
-  const int max_groups = 148 / cg;
+  int max_groups = 148 / cg;
+  if (group_limit > 0 && group_limit < max_groups) max_groups = group_limit;
   const int tiles_m = (M + G2_BM * cg - 1) / (G2_BM * cg);
-  const double SETUP = 3500.0, EPI_CHUNK = 1250.0, SM_BW = 90.0, L2_BW = 6000.0, MEMSET = 4000.0;
+  const double SETUP = 3500.0, EPI_CHUNK = 1450.0, SM_BW = 58.0, L2_BW = 11000.0, MEMSET = 4000.0, FIX = 2500.0;
+  static const int force_sk = [] { const char* e = getenv("FXN_GEMM_FORCE_STREAMK"); return e ? atoi(e) : 0; }();
+  static const int no_fix = [] { const char* e = getenv("FXN_GEMM_NO_FIXUP"); return e ? atoi(e) : 0; }();
   Plan best{};
   double best_t = 1e300;
   for (int bn = unit; bn <= 256; bn += unit) {
@@ -639,10 +820,12 @@ Plan make_plan(int M, int N, int K, int nterms, int b_mn, bool plain_c, int forc
     if (stages > G2_MAX_STAGES) stages = G2_MAX_STAGES;
     if (stages < 2) continue;
     const long long tiles = static_cast<long long>(tiles_m) * tiles_n;
-    const double t_mma = nterms * 4.0 * (bn / 2.0);
+    const double t_mma = nterms * 4.0 * (bn / 2.0) + 90.0;
     const double t_epi = EPI_CHUNK * ((bn + 31) / 32);
-    for (int mode = 0; mode < 2; ++mode) {                     // 0 = whole tiles, 1 = stream-K
-      if (mode == 1 && (!plain_c || kb_total < 4)) break;
+    for (int mode = 0; mode < 3; ++mode) {
+      if (mode == 1 && (!plain_c || kb_total < 4)) continue;
+      if (mode == 2 && (plain_c || !fix_ok || no_fix || kb_total < 8 || bn % 32 != 0)) continue;
+      if (mode == 0 && force_sk && plain_c && kb_total >= 4) continue;
       int groups;
       double t;
       if (mode == 0) {
@@ -653,13 +836,19 @@ Plan make_plan(int M, int N, int K, int nterms, int b_mn, bool plain_c, int forc
         t = SETUP + t_main + (tpg - 1) * fmax(t_main, t_epi) + t_epi;
       } else {
         const long long units = tiles * kb_total;
-        const long long g = units / 2;
+        const long long g = units / (mode == 2 ? 4 : 2);     // every group gets several k-blocks
         groups = static_cast<int>(g < max_groups ? g : max_groups);
-        if (groups < 1) break;
+        if (groups < 1) continue;
         const double kb_per = static_cast<double>(units) / groups;
         const double t_load = fmax(stage_bytes / SM_BW, static_cast<double>(stage_bytes) * groups * cg / L2_BW);
-        const double segs = 1.0 + (kb_per < kb_total ? 1.0 : kb_per / kb_total);
-        t = SETUP + MEMSET + kb_per * fmax(t_mma, t_load) + segs * 1.3 * t_epi;
+        if (mode == 1) {
+          const double segs = 1.0 + (kb_per < kb_total ? 1.0 : kb_per / kb_total);
+          t = SETUP + MEMSET + kb_per * fmax(t_mma, t_load) + segs * 0.7 * t_epi;
+        } else {
+          // one exposed owner epilogue (reads its slot), the contributor's register-order reductions are short
+          const double split = (tiles % groups == 0) ? 0.0 : 1.0;
+          t = SETUP + kb_per * fmax(t_mma, t_load) + t_epi * (1.0 + 0.35 * split) + FIX * split;
+        }
       }
       if (t < best_t) {
         best_t = t;
@@ -712,13 +901,24 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
   p.b_mn = d->b_mn_major ? 1 : 0;
   p.nterms = d->nterms;
   const bool plain_c = (d->splitk < 0 || d->splitk > 1) && d->C && !d->c_hi && !d->colstats && !d->epi_act && !d->accumulate && !d->mse_x;
-  const Plan pl = make_plan(d->M, d->N, d->K, d->nterms, p.b_mn, plain_c, d->block_n);
+  const bool fix_ok = d->fix_ws != nullptr && d->fix_flags != nullptr;
+  Plan pl = make_plan(d->M, d->N, d->K, d->nterms, p.b_mn, plain_c, d->block_n, fix_ok, d->max_groups);
   if (pl.stages < 1) return set_error(FXN_ERR_ARG, "fxn_gemm: tile does not fit in shared memory");
+  if (pl.streamk == 2) {
+    // one slot per group: [cg][4][ceil(bn / 32)][1024] floats; two flag words per group
+    const long long need = static_cast<long long>(pl.groups) * pl.cg * 4 * ((pl.bn + 31) / 32) * 1024 * sizeof(float);
+    if (d->fix_ws_bytes < need || d->fix_flags_count < 2LL * pl.groups)
+      pl = make_plan(d->M, d->N, d->K, d->nterms, p.b_mn, plain_c, d->block_n, false, d->max_groups);   // workspace too small
+  }
+  p.fix_ws = d->fix_ws;
+  p.fix_flags = static_cast<unsigned*>(d->fix_flags);
   p.bn = pl.bn;
   p.stages = pl.stages;
   p.streamk = pl.streamk;
   p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n;
   p.kb_total = (d->K + G2_BK - 1) / G2_BK;
+  static const int force_stages = [] { const char* e = getenv("FXN_GEMM_STAGES"); return e ? atoi(e) : 0; }();
+  if (force_stages > 0 && force_stages < p.stages) p.stages = force_stages;      // experiments: pipeline depth
   if (p.stages > p.kb_total && !p.streamk && static_cast<long long>(pl.tiles_m) * pl.tiles_n <= pl.groups)
     p.stages = p.kb_total < 1 ? 1 : p.kb_total;                 // one tile per group: no need for more stages than k-blocks
   uint32_t tc = 32;
@@ -746,7 +946,7 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
   p.stats_alpha = d->stats_alpha == 0.f ? 1.f : d->stats_alpha;
   p.stats_alpha_dev = d->stats_alpha_dev;
   {
-    const int cmode = !d->C ? 0 : (p.streamk ? 3 : (d->accumulate ? 2 : 1));
+    const int cmode = !d->C ? 0 : (p.streamk == 1 ? 3 : (d->accumulate ? 2 : 1));
     const int act = p.epi_act, st = p.stats_mode;
     const bool pl_ = p.c_hi != nullptr, ms = p.mse_x != nullptr;
     struct V { int act, cmode, planes, stats, mse; };
@@ -783,7 +983,7 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(d->colstats, 0, sizeof(float) * d->N, stream);
     if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "colsum memset: %s", cudaGetErrorString(e));
   }
-  if (p.streamk && !d->outputs_prezeroed) {
+  if (p.streamk == 1 && !d->outputs_prezeroed) {
     cudaError_t e = cudaMemset2DAsync(d->C, d->ldc * sizeof(float), 0, d->N * sizeof(float), d->M, stream);
     if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "stream-K memset: %s", cudaGetErrorString(e));
   }
@@ -794,7 +994,7 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
   // prefetch (or at least 3).
   static const int epi_env = [] { const char* e = getenv("FXN_GEMM_EPI_WARPS"); return e ? atoi(e) : 4; }();
   int ew = 4;
-  if (epi_env == 8 && !p.streamk && p.kb_total <= 16) {
+  if (epi_env == 8 && !p.streamk && p.kb_total <= 16) {      // (the fix-up protocol counts four epilogue warps per CTA)
     int st8 = (G2_MAX_DYN_SMEM - 1024 - 2 * G2_STG_BYTES) / stage_bytes;
     if (st8 > p.stages) st8 = p.stages;
     if (st8 >= 3 || (st8 >= 2 && st8 >= p.kb_total)) { ew = 8; p.stages = st8; }
@@ -820,7 +1020,11 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
 extern "C" int fxn_gemm_plan(int M, int N, int K, int nterms, int b_mn_major, int plain_c, int block_n, int* out8) {
   if (!out8 || M <= 0 || N <= 0 || K <= 0 || (nterms != 1 && nterms != 3))
     return fxn::set_error(FXN_ERR_ARG, "fxn_gemm_plan: bad argument");
-  const Plan pl = make_plan(M, N, K, nterms, b_mn_major ? 1 : 0, plain_c != 0, block_n);
+  // plain_c: 0 = fused epilogue, whole tiles only; 1 = plain fp32 C (stream-K eligible); 2 = fused epilogue with a fix-up
+  // workspace (stream-K with fix-up eligible). block_n may carry a group limit in its upper half: block_n | limit << 16.
+  const int limit = block_n >> 16;
+  block_n &= 0xFFFF;
+  const Plan pl = make_plan(M, N, K, nterms, b_mn_major ? 1 : 0, plain_c == 1, block_n, plain_c == 2, limit);
   if (pl.stages < 1) return fxn::set_error(FXN_ERR_ARG, "fxn_gemm_plan: tile does not fit in shared memory");
   const int nplanes = nterms == 3 ? 2 : 1;
   const int stage_bytes = nplanes * (G2_BM * G2_BK * 2 + (pl.bn / pl.cg) * G2_BK * 2);
@@ -853,3 +1057,20 @@ extern "C" int fxn_debug_gemm_trace(long long* out32) {
     for (int i = 0; i < 16; ++i) out32[c * 16 + i] = h[c][i] ? h[c][i] - h[c][0] : -1;
   return 0;
 }
+
+extern "C" int fxn_gemm(const fxn_gemm_desc* d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d) return fxn::set_error(FXN_ERR_ARG, "null descriptor");
+  if (d->M <= 0 || d->N <= 0 || d->K <= 0) return fxn::set_error(FXN_ERR_ARG, "fxn_gemm: M,N,K must be positive");
+  if (d->nterms != 1 && d->nterms != 3) return fxn::set_error(FXN_ERR_ARG, "fxn_gemm: nterms must be 1 or 3");
+  if (!d->a_hi || !d->b_hi || (d->nterms == 3 && (!d->a_lo || !d->b_lo)))
+    return fxn::set_error(FXN_ERR_ARG, "fxn_gemm: missing operand plane");
+  if (!d->C && !d->c_hi) return fxn::set_error(FXN_ERR_ARG, "fxn_gemm: no output");
+  return fxn::gemm2_dispatch(d, stream);
+}
+
+extern "C" int fxn_gemm_stat_tiles(int M) { return (M + fxn::G2_BM - 1) / fxn::G2_BM; }
+
+// Bytes of fix-up workspace / number of 32-bit flag words that cover every plan fxn_gemm can choose.
+extern "C" long long fxn_gemm_fix_ws_bytes(void) { return 74LL * 2 * 4 * 8 * 1024 * static_cast<long long>(sizeof(float)); }
+extern "C" int fxn_gemm_fix_flag_words(void) { return 2 * 148; }

@@ -23,40 +23,63 @@ def pad128(n: int) -> int:
     return (int(n) + 127) // 128 * 128
 
 
-def concurrent_tile_widths(rows: int, widths: Sequence[int], depths: Sequence[int], sms: int = 148) -> List[int]:
-    """Tile widths (fxn_gemm block_n) for the first-layer GEMMs of several modalities that run as PARALLEL graph branches.
-    Left alone, each GEMM plans for the whole chip (128-wide tiles on ~128 SMs) and the two launches queue behind each
-    other; their 128-wide tiles are also bound by shared-memory ingest (~42 B/clk/SM measured: 48 KB per k-block against
-    768 MMA cycles). Wider tiles on fewer SMs are MMA-bound and let the branches really overlap. Model per k-block of one
-    CTA pair tile [256 x bn] with the 3-term split: MMA 6*bn cycles, ingest (32768 + 128*bn) / 42 cycles; the choice
-    minimises the slowest branch subject to all CTAs being co-resident (one CTA per SM). Returns 0 (= library default)
-    when there is a single branch."""
-    if len(widths) < 2:
-        return [0] * len(widths)
+def concurrent_plan(rows: int, widths: Sequence[int], depths: Sequence[int], pairs: int = 74):
+    """(block_n, max_groups) per first-layer GEMM of several modalities that run as PARALLEL graph branches: tile widths and
+    a division of the chip's 74 SM pairs that minimise the makespan of whole-tile launches. Left alone each GEMM plans for
+    the whole chip and the launches queue behind each other. Cost of one k-block of a [256 x bn] pair tile (measured,
+    profiles/r02_bn_sweep_after.log): max(6 bn + 90 MMA cycles, (32768 + 128 bn) / 58 ingest cycles), x1.25 when the
+    streamed operand comes from HBM (a batch larger than L2); a tile adds ~9000 cycles of set-up / pipeline fill and
+    1450 cycles of epilogue per 32 columns. Returns [(0, 0)] (= library defaults) for a single branch."""
+    n = len(widths)
+    if n < 2:
+        return [(0, 0)] * n
     import itertools
     mt = (rows + 255) // 256
     cands = []
     for h, d in zip(widths, depths):
         opts = []
-        for bn in range(32, 257, 32):
+        for bn in range(64, 257, 32):
             tn = (h + bn - 1) // bn
             if tn > 1 and (tn - 1) * bn >= h:
                 continue
             kb = (d + 63) // 64
-            t = kb * max(6.0 * bn, (32768.0 + 128.0 * bn) / 42.0) + 9000.0 + 1450.0 * (bn // 32)
-            opts.append((bn, 2 * mt * tn, t))
+            t = kb * max(6.0 * bn + 90.0, (32768.0 + 128.0 * bn) / 58.0) * 1.25 + 9000.0 + 1450.0 * (bn // 32)
+            opts.append((bn, mt * tn, t))
         cands.append(opts)
     best, best_t = None, None
     for combo in itertools.product(*cands):
-        ctas = sum(c[1] for c in combo)
-        if ctas > sms:
-            continue
-        t = max(c[2] for c in combo)
-        if best_t is None or t < best_t or (t == best_t and ctas < sum(c[1] for c in best)):
-            best, best_t = combo, t
+        # smallest makespan T for which the groups needed, sum_i ceil(tiles_i / floor(T / t_i)), fit on the chip
+        ts = sorted({r * c[2] for c in combo for r in range(1, c[1] + 1)})
+        for T in ts:
+            need = [-(-c[1] // int(T // c[2])) if T >= c[2] else None for c in combo]
+            if None in need or sum(need) > pairs:
+                continue
+            if best_t is None or T < best_t:
+                best, best_t = [(c[0], g) for c, g in zip(combo, need)], T
+            break
     if best is None:
-        return [0] * len(widths)
-    return [c[0] for c in best]
+        return [(0, 0)] * n
+    # spare pairs go to the branch that ends last
+    spare = pairs - sum(g for _, g in best)
+    if spare > 0:
+        bn0, g0 = best[0]
+        best[0] = (bn0, g0 + spare)
+    return best
+
+
+def split_groups(costs: Sequence[float], total: int = 74) -> List[int]:
+    """CTA-group budgets (fxn_gemm max_groups) for GEMMs that run as parallel graph branches: the chip's 74 SM pairs are
+    divided in proportion to the MMA work of each launch, so that stream-K launches finish together instead of queueing
+    behind each other. A single launch gets 0 (= no cap)."""
+    if len(costs) < 2:
+        return [0] * len(costs)
+    tot = float(sum(costs)) or 1.0
+    g = [max(2, int(round(total * c / tot))) for c in costs]
+    while sum(g) > total:
+        g[g.index(max(g))] -= 1
+    while sum(g) < total:
+        g[g.index(max(g))] += 1
+    return g
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -565,6 +588,9 @@ class TrunkEngine(EngineBase):
                 self.wplanes.add_segment("fusion_block.weight", i * self.latent, self.latent, self.latent,
                                          self.n * self.latent, self.wf_off + i * Lp, self.n * Lp)
         self._finish_init(self.n - 1)
+        # stream-K fix-up workspaces of the first-layer GEMMs (one per modality branch: the branches overlap in time)
+        self.fix = [L.FixWorkspace(self.device) for _ in range(self.n)]
+        self.wgrad_groups = split_groups([((self.h[i] + 255) // 256) * ((self.d[i] + 255) // 256) for i in range(self.n)])
 
     def wf_planes(self, i: Optional[int] = None) -> Planes:
         full = self.wplanes.planes(self.wf_off, self.latent, self.n * self.Lp, self.n * self.Lp)
@@ -618,7 +644,7 @@ class TrunkEngine(EngineBase):
         B, Bp, R, G = ws["B"], ws["Bp"], ws["R"], self.G
         mt = L.stat_tiles(Bp)
         tags = [""] if G == 1 else ["anchor.", "positive.", "negative."]
-        bns = concurrent_tile_widths(R, self.h, self.d) if self.parallel_encoders else [0] * self.n
+        plan = concurrent_plan(R, self.h, self.d) if self.parallel_encoders else [(0, 0)] * self.n
         self._fork()
         for i in range(self.n):
           with torch.cuda.stream(self._stream_for(i)):
@@ -627,7 +653,8 @@ class TrunkEngine(EngineBase):
               use_epi_stats = train and G == 1
               L.gemm(R, h, self.d[i], ws["X"][i], 0, self.wp(self.w1[i]), 0, C_ptr=ws["Z"][i].data_ptr(), ldc=hp,
                      bias=a.p(f"encoders.{i}.layer_1.bias"),
-                     colstats=ws["partials"][i].data_ptr() if use_epi_stats else None, stats_mode=2, block_n=bns[i])
+                     colstats=ws["partials"][i].data_ptr() if use_epi_stats else None, stats_mode=2,
+                     block_n=plan[i][0], max_groups=plan[i][1], fix=self.fix[i] if self.n == 1 else None)
               for g in range(G):
                   r0 = g * Bp
                   if train and G > 1:
@@ -696,10 +723,15 @@ class TrunkEngine(EngineBase):
                                    dbeta=a.view(f"encoders.{i}.batchnorm.bias", a.grad),
                                    accumulate_affine=0 if first else 1,   # affine grads add up over the three triplet passes
                                    dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld, prezeroed=pz)
-              # dW1_i = dZ_i^T * X_i
-              L.gemm(h, self.d[i], R, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_1.weight"),
-                     ldc=self.d[i], splitk=-1, prezeroed=pz)
               self._aux_join(i)
+        self._join()
+        # dW1_i = dZ_i^T * X_i: the big weight gradients of all modalities start TOGETHER, each stream-K launch on its
+        # share of the SM pairs (left to themselves they would each take the whole chip and run back to back)
+        self._fork()
+        for i in range(self.n):
+            with torch.cuda.stream(self._stream_for(i)):
+                L.gemm(self.h[i], self.d[i], R, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_1.weight"),
+                       ldc=self.d[i], splitk=-1, prezeroed=pz, max_groups=self.wgrad_groups[i] if self.parallel_encoders else 0)
         self._join()
         self._aux_join(len(self.aux) - 1)          # the heads' weight gradients
 

@@ -85,6 +85,14 @@ typedef struct fxn_gemm_desc {
    * column sums): the library then queues no memset in front of the kernel (the engine zeroes its whole gradient arena
    * once per step, beside the forward pass) */
   int outputs_prezeroed;
+  /* Scheduling. max_groups > 0 caps the number of CTA groups (pairs of SMs) the launch may occupy: the engine splits the
+   * chip between GEMMs it runs concurrently. fix_ws / fix_flags (optional; fxn_gemm_fix_ws_bytes() bytes and
+   * fxn_gemm_fix_flag_words() 32-bit words; the flags zeroed ONCE by the caller; both private to launches that cannot
+   * overlap in time) allow stream-K for problems with a fused epilogue: partial accumulators of a split tile travel through
+   * the workspace and the group holding the tile's last k-block runs the epilogue; the library leaves the flags zeroed. */
+  int max_groups;
+  float* fix_ws; long long fix_ws_bytes;
+  void* fix_flags; long long fix_flags_count;
 } fxn_gemm_desc;
 int fxn_gemm(const fxn_gemm_desc* d, void* stream);
 /* Debug aid: with FXN_GEMM_TRACE=1 in the environment the persistent kernel stamps clock64 at its pipeline milestones
@@ -94,9 +102,13 @@ int fxn_debug_gemm_trace(long long* out32);
  * last traced launch -- shows scheduling waves and stragglers. */
 int fxn_debug_gemm_cta_times(long long* start_ns, long long* end_ns, int n);
 int fxn_gemm_stat_tiles(int M);
+long long fxn_gemm_fix_ws_bytes(void);
+int fxn_gemm_fix_flag_words(void);
 /* The launch plan fxn_gemm would choose (host-side cost model, no device needed): out8 = {cta_group, block_n, stages,
- * streamk, groups, tiles_m, tiles_n, dynamic shared memory bytes}. plain_c != 0: the output is a plain fp32 C (stream-K
- * eligible); block_n > 0 forces the tile width as fxn_gemm_desc.block_n does. */
+ * streamk, groups, tiles_m, tiles_n, dynamic shared memory bytes}. plain_c = 1: the output is a plain fp32 C (stream-K
+ * eligible); plain_c = 2: fused epilogue with a fix-up workspace (stream-K with fix-up eligible, streamk = 2 in the plan);
+ * block_n & 0xFFFF > 0 forces the tile width as fxn_gemm_desc.block_n does, block_n >> 16 > 0 caps the groups as
+ * fxn_gemm_desc.max_groups does. */
 int fxn_gemm_plan(int M, int N, int K, int nterms, int b_mn_major, int plain_c, int block_n, int* out8);
 
 /* ---- BatchNorm1d (+ activation + dropout) ----

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import flexynesis_b200 as fx
-from flexynesis_b200.engine import concurrent_tile_widths
+from flexynesis_b200.engine import concurrent_plan, split_groups
 from flexynesis_b200.trials import run_trials
 
 
@@ -56,13 +56,17 @@ def test_run_trials_spreads_trials_over_devices_and_keeps_order():
         run_trials(_objective, [{"x": 1}, {"x": 2, "boom": True}], devices=["cpu:0"], timeout=120)
 
 
-def test_concurrent_tile_widths():
-    assert concurrent_tile_widths(4096, [512], [5000]) == [0]                   # a single branch plans for the whole chip
-    bns = concurrent_tile_widths(4096, [512, 307], [5000, 3000])                # config 2: both branches co-resident
-    assert bns == [256, 160]
-    mt = 4096 // 256
-    assert sum(2 * mt * -(-h // bn) for h, bn in zip([512, 307], bns)) <= 148
-    assert concurrent_tile_widths(32768, [512, 307], [5000, 3000]) == [0, 0]    # no co-resident plan: library default
+def test_concurrent_plan():
+    assert concurrent_plan(4096, [512], [5000]) == [(0, 0)]                     # a single branch plans for the whole chip
+    plan = concurrent_plan(4096, [512, 307], [5000, 3000])                      # config 2: the branches share the 74 SM pairs
+    assert sum(g for _, g in plan) == 74 and all(g >= 2 for _, g in plan)
+    for (bn, g), h in zip(plan, [512, 307]):
+        assert bn % 32 == 0 and 64 <= bn <= 256
+        tn = -(-h // bn)
+        assert (tn - 1) * bn < h                                                # no tile column lies entirely outside N
+    assert plan[0][1] > plan[1][1]                                              # the bigger contraction gets more of the chip
+    assert split_groups([3.0, 1.0]) == [56, 18] and split_groups([1.0]) == [0]
+    assert sum(split_groups([5.0, 3.0, 1.0])) == 74
 
 
 def test_vae_feature_importance_satisfies_completeness():

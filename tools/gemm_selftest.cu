@@ -46,6 +46,8 @@ __global__ void ref_gemm_kernel(const float* A, long long lda, int a_mn, const f
 
 struct Case {
   int M, N, K, a_mn, b_mn, nterms, bias, splitk, stats, planes, block_n;
+  int fix = 0;         // 1: give the call a fix-up workspace (stream-K with a fused epilogue)
+  int groups = 0;      // fxn_gemm_desc.max_groups
 };
 
 static long long r8(long long x) { return (x + 7) / 8 * 8; }
@@ -93,6 +95,18 @@ static int run_case(const Case& c, bool verbose) {
   d.c_hi = Ch; d.c_lo = Cl; d.ldp = ldp;
   d.colstats = stats; d.stats_mode = 2;
   d.splitk = c.splitk; d.block_n = c.block_n;
+  d.max_groups = c.groups;
+  float* fix_ws = nullptr; unsigned* fix_flags = nullptr;
+  const long long fix_bytes = fxn_gemm_fix_ws_bytes();
+  const int fix_words = fxn_gemm_fix_flag_words();
+  if (c.fix) {
+    CK(cudaMalloc(&fix_ws, fix_bytes)); CK(cudaMemset(fix_ws, 0, fix_bytes));
+    CK(cudaMalloc(&fix_flags, fix_words * 4)); CK(cudaMemset(fix_flags, 0, fix_words * 4));
+    d.fix_ws = fix_ws; d.fix_ws_bytes = fix_bytes; d.fix_flags = fix_flags; d.fix_flags_count = fix_words;
+    rc = fxn_gemm(&d, 0);             // a first launch: the checked one below must find the workspace handed back clean
+    if (rc) { printf("fxn_gemm failed: %s\n", fxn_last_error()); return 1; }
+    CK(cudaMemset(C, 0xFF, (long long)c.M * ldc * 4));
+  }
   rc = fxn_gemm(&d, 0);
   if (rc) { printf("fxn_gemm failed: %s\n", fxn_last_error()); return 1; }
   dim3 rb(32, 8), rg((c.N + 31) / 32, (c.M + 7) / 8);
@@ -123,6 +137,14 @@ static int run_case(const Case& c, bool verbose) {
       unsigned u; memcpy(&u, &hC[(size_t)m * ldc + n], 4);
       if (u != 0xFFFFFFFFu) { ok = false; printf("  C padding overwritten at (%d,%lld)\n", m, n); break; }
     }
+  if (c.fix && ok) {
+    std::vector<float> hw(fix_bytes / 4);
+    std::vector<unsigned> hf(fix_words);
+    CK(cudaMemcpy(hw.data(), fix_ws, fix_bytes, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hf.data(), fix_flags, fix_words * 4, cudaMemcpyDeviceToHost));
+    (void)hw;
+    for (unsigned v : hf) if (v != 0u) { ok = false; printf("  fix-up flags not reset\n"); break; }
+  }
   double perr = 0, serr = 0;
   if (c.planes && ok) {
     std::vector<__nv_bfloat16> hh((size_t)c.M * ldp), hl((size_t)c.M * ldp);
@@ -154,9 +176,10 @@ static int run_case(const Case& c, bool verbose) {
     if (serr > 1e-5) ok = false;
   }
   if (verbose || !ok)
-    printf("%s M=%d N=%d K=%d a_mn=%d b_mn=%d terms=%d bias=%d splitk=%d bn=%d  relrms=%.3e maxerr/rms=%.3e planes=%.2e stats=%.2e\n",
-           ok ? "PASS" : "FAIL", c.M, c.N, c.K, c.a_mn, c.b_mn, c.nterms, c.bias, c.splitk, c.block_n, relrms,
-           maxerr / rms, perr / rms, serr);
+    printf("%s M=%d N=%d K=%d a_mn=%d b_mn=%d terms=%d bias=%d splitk=%d bn=%d fix=%d groups=%d  relrms=%.3e maxerr/rms=%.3e planes=%.2e stats=%.2e\n",
+           ok ? "PASS" : "FAIL", c.M, c.N, c.K, c.a_mn, c.b_mn, c.nterms, c.bias, c.splitk, c.block_n, c.fix, c.groups,
+           relrms, maxerr / rms, perr / rms, serr);
+  if (fix_ws) { cudaFree(fix_ws); cudaFree(fix_flags); }
   cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(Cref); cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl);
   if (bias) cudaFree(bias);
   if (stats) cudaFree(stats);
@@ -193,6 +216,13 @@ static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn
   d.a_hi = Ah; d.a_lo = Al; d.lda = lda; d.a_mn_major = a_mn;
   d.b_hi = Bh; d.b_lo = Bl; d.ldb = ldb; d.b_mn_major = b_mn;
   d.nterms = nterms; d.C = C; d.ldc = N; d.block_n = block_n; d.splitk = splitk;
+  float* fix_ws = nullptr; unsigned* fix_flags = nullptr;
+  if (getenv("FXN_BENCH_FIX")) {
+    CK(cudaMalloc(&fix_ws, fxn_gemm_fix_ws_bytes())); CK(cudaMemset(fix_ws, 0, fxn_gemm_fix_ws_bytes()));
+    CK(cudaMalloc(&fix_flags, fxn_gemm_fix_flag_words() * 4)); CK(cudaMemset(fix_flags, 0, fxn_gemm_fix_flag_words() * 4));
+    d.fix_ws = fix_ws; d.fix_ws_bytes = fxn_gemm_fix_ws_bytes(); d.fix_flags = fix_flags; d.fix_flags_count = fxn_gemm_fix_flag_words();
+    if (getenv("FXN_BENCH_GROUPS")) d.max_groups = atoi(getenv("FXN_BENCH_GROUPS"));
+  }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) fxn_gemm(&d, 0);
@@ -225,6 +255,7 @@ static void bench_case(const char* name, int M, int N, int K, int a_mn, int b_mn
     }
   }
   cudaFree(Ah); cudaFree(Al); cudaFree(Bh); cudaFree(Bl); cudaFree(C);
+  if (fix_ws) { cudaFree(fix_ws); cudaFree(fix_flags); }
 }
 
 int main(int argc, char** argv) {
@@ -265,12 +296,26 @@ int main(int argc, char** argv) {
       {307, 3000, 1000, 1, 1, 3, 1, -1, 0, 0, 0},  // stream-K, ragged, with bias
       {4096, 128, 8000, 0, 0, 3, 1, -1, 0, 0, 0},  // stream-K, K-major, long K
       {100, 1000, 4096, 1, 1, 3, 0, -1, 0, 0, 0},  // single-CTA groups (M <= 128) with stream-K
+      // stream-K with fix-up: fused epilogues (bias + BN partials + planes) on split tiles
+      {1024, 512, 5000, 0, 0, 3, 1, 1, 1, 1, 0, 1, 0},    // config 2 encoder forward (M reduced): 8 tiles over 74 groups
+      {4096, 512, 5000, 0, 0, 3, 1, 1, 1, 0, 0, 1, 54},   // the full layer on 54 groups (as launched beside encoder 1)
+      {4096, 307, 3000, 0, 0, 3, 1, 1, 1, 1, 0, 1, 20},   // encoder 1 on 20 groups, ragged N
+      {333, 300, 2000, 0, 0, 3, 1, 1, 1, 1, 0, 1, 7},     // ragged M / N / K, tiles split three ways
+      {512, 128, 1000, 0, 0, 3, 1, 1, 1, 1, 0, 1, 0},     // config 1 encoder
+      {100, 96, 3000, 0, 0, 3, 1, 1, 1, 1, 0, 1, 0},      // single-CTA groups (M <= 128)
+      {2048, 1024, 4096, 0, 1, 3, 0, 1, 0, 1, 0, 1, 37},  // B MN-major (dgrad), odd group count
   };
   int fails = 0;
   for (const Case& c : cases) fails += run_case(c, true);
   printf("%s: %d/%zu cases failed\n", fails ? "SELFTEST FAILED" : "SELFTEST OK", fails, cases.size());
   if (argc > 1 && !strcmp(argv[1], "bench") && !fails) {
     bench_case("cfg2 enc0 fwd", 4096, 512, 5000, 0, 0, 3, 256, 1);
+    setenv("FXN_BENCH_FIX", "1", 1);
+    bench_case("cfg2 enc0 fwd fix-up", 4096, 512, 5000, 0, 0, 3, 0, 0);
+    bench_case("cfg2 enc1 fwd fix-up", 4096, 307, 3000, 0, 0, 3, 0, 0);
+    bench_case("cfg5 enc fwd fix-up", 4096, 1024, 24000, 0, 0, 3, 0, 0);
+    bench_case("cfg3 decoder out fix-up", 4096, 5000, 512, 0, 0, 3, 0, 0);
+    unsetenv("FXN_BENCH_FIX");
     bench_case("cfg2 enc0 fwd bn128", 4096, 512, 5000, 0, 0, 3, 128, 1);
     bench_case("cfg2 enc0 fwd splitk2", 4096, 512, 5000, 0, 0, 3, 256, 2);
     bench_case("cfg2 enc0 fwd 1-term", 4096, 512, 5000, 0, 0, 1, 256, 1);
