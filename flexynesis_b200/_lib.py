@@ -71,6 +71,34 @@ class BnBwdDesc(C.Structure):
     ]
 
 
+HEADS_MAX_VARS = 8
+
+
+class HeadsVar(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int), ("C", C.c_int), ("slot", C.c_int),
+        ("W1", C.c_void_p), ("b1", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+        ("Wout", C.c_void_p), ("bout", C.c_void_p), ("y", C.c_void_p), ("logits", C.c_void_p),
+        ("mask", C.c_void_p), ("ldm", c_ll), ("seed", C.c_ulonglong), ("log_var", C.c_void_p),
+        ("dWout", C.c_void_p), ("dbout", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+    ]
+
+
+class HeadsDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("L", C.c_int), ("sh", C.c_int), ("nv", C.c_int),
+        ("F", C.c_void_p), ("ldf", c_ll), ("Zh", C.c_void_p), ("ldz", c_ll), ("G", C.c_void_p), ("ldg", c_ll),
+        ("partials", C.c_void_p), ("saved", C.c_void_p), ("sums", C.c_void_p), ("acc", C.c_void_p),
+        ("train", C.c_int), ("p_drop", C.c_float), ("momentum", C.c_float), ("eps", C.c_float),
+        ("seed_dev", C.c_void_p), ("backward", C.c_int),
+        ("var", HeadsVar * HEADS_MAX_VARS),
+        ("dz_hi", C.c_void_p), ("dz_lo", C.c_void_p), ("ldzp", c_ll),
+        ("df_hi", C.c_void_p), ("df_lo", C.c_void_p), ("ldfp", c_ll),
+        ("dF", C.c_void_p), ("lddf", c_ll), ("dbias", C.c_void_p), ("zero_dbias", C.c_int),
+    ]
+
+
 def _load():
     if not os.path.isfile(LIB_PATH):
         raise ImportError(
@@ -90,7 +118,7 @@ lib = _load()
 SYMBOLS = [
     "fxn_version", "fxn_last_error", "fxn_launch_count", "fxn_reset_launch_count", "fxn_split_planes", "fxn_gemm",
     "fxn_gemm_stat_tiles", "fxn_gemm_plan", "fxn_gemm_fix_ws_bytes", "fxn_gemm_fix_flag_words", "fxn_bn_act_fwd", "fxn_bn_act_bwd", "fxn_col_stats", "fxn_head_out_fwd", "fxn_head_out_bwd",
-    "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
+    "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_heads_fused_ok", "fxn_heads_fwd", "fxn_heads_bwd", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
     "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn", "fxn_gcn_fwd", "fxn_gcn_bwd",
     "fxn_merge_col_stats", "fxn_node_lin_fwd", "fxn_node_lin_bwd", "fxn_debug_gemm_trace", "fxn_debug_gemm_cta_times", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast",
@@ -263,6 +291,18 @@ def head_out_bwd(D, ldd, rows, sh, W, Cc, logits, ldl, kind, y, acc, coef, weigh
                                C.c_void_p(logits), c_ll(ldl), C.c_int(kind), C.c_void_p(y), C.c_void_p(acc),
                                C.c_void_p(coef), C.c_void_p(weight), C.c_void_p(dD), c_ll(ldg), C.c_void_p(dW),
                                C.c_void_p(dbias), C.c_int(int(prezeroed)), C.c_void_p(stream())), "fxn_head_out_bwd")
+
+
+def heads_fused_ok(Lt: int, sh: int, nv: int, max_c: int) -> bool:
+    return bool(lib.fxn_heads_fused_ok(C.c_int(Lt), C.c_int(sh), C.c_int(nv), C.c_int(max_c)))
+
+
+def heads_fwd(desc: HeadsDesc) -> None:
+    check(lib.fxn_heads_fwd(C.byref(desc), C.c_void_p(stream())), "fxn_heads_fwd")
+
+
+def heads_bwd(desc: HeadsDesc) -> None:
+    check(lib.fxn_heads_bwd(C.byref(desc), C.c_void_p(stream())), "fxn_heads_bwd")
 
 
 def cox_fwd(o, ldo, durations, events, n, coef, acc) -> None:

@@ -82,6 +82,25 @@ def split_groups(costs: Sequence[float], total: int = 74) -> List[int]:
     return g
 
 
+def split_groups_tiles(tiles: Sequence[int], total: int = 74, split_penalty: float = 1.25) -> List[int]:
+    """Division of the SM pairs between concurrent stream-K launches (the first-layer weight gradients) given their tile
+    counts (all tiles equally deep): a share that divides its tile count runs whole rounds (no split tile, no reduction
+    traffic), any other share pays ~25 % for the partial-tile reductions (measured: 80 + 48 tiles run 92 us as 40 + 34
+    pairs, 101 us as the proportional 46 + 28; profiles/r02_pair_exp_wgrad.log). Two launches are searched exhaustively,
+    more fall back to the proportional split."""
+    n = len(tiles)
+    if n < 2:
+        return [0] * n
+    if n > 2:
+        return split_groups(tiles, total)
+
+    def cost(t, g):
+        return -(-t // g) if t % g == 0 else split_penalty * t / g
+    best = min(range(2, total - 1), key=lambda g0: (max(cost(tiles[0], g0), cost(tiles[1], total - g0)),
+                                                     cost(tiles[0], g0) + cost(tiles[1], total - g0)))
+    return [best, total - best]
+
+
 # ----------------------------------------------------------------------------------------------------
 # flat parameter arena
 # ----------------------------------------------------------------------------------------------------
@@ -279,17 +298,80 @@ class HeadsBlock:
         ws["acc"] = torch.zeros(max(self.n_losses, 1), 2, device=dev)
         ws["out"] = torch.zeros(2 * max(self.n_losses, 1) + 2, device=dev)
         ws["coef"] = torch.zeros(B, device=dev)
+        # fused narrow-head path (csrc/heads_fused.cu)
+        ws["hf_partials"] = torch.zeros(2 * w * ((((B + 15) // 16) + 31) // 32 * 32), device=dev)
+        ws["hf_saved"] = torch.zeros(2 * w, device=dev)
+        ws["hf_sums"] = torch.zeros(2 * w, device=dev)
         return ws
 
     def w1_planes(self) -> Planes:
         return self.eng.wplanes.planes(self.w1_off, max(self.width, 1), self.L, self.Lp)
 
+    # ---- fused narrow-head path ----
+    def fused(self) -> bool:
+        """All heads narrow, MSE / cross-entropy only, no global-batch sync: the head section runs as three CUDA-core
+        kernels (fxn_heads_fwd / fxn_heads_bwd) instead of the generic GEMM + BatchNorm + output-layer launches."""
+        if getattr(self, "_fused_ok", None) is None:
+            self._fused_ok = (bool(self.vars) and all(k in (1, 2) for k in self.kinds.values())
+                              and L.heads_fused_ok(self.L, self.sh, len(self.vars), max(self.C.values()))
+                              and not int(__import__("os").environ.get("FXN_NO_FUSED_HEADS", "0")))
+        return self._fused_ok and self.eng.sync is None
+
+    def _desc(self, ws, F32: torch.Tensor, B: int, y, train: bool, masks, with_loss: bool, backward: bool) -> "L.HeadsDesc":
+        eng, a, model = self.eng, self.eng.arena, self.eng.model
+        d = L.HeadsDesc()
+        d.B, d.L, d.sh, d.nv = B, self.L, self.sh, len(self.vars)
+        d.F, d.ldf = F32.data_ptr(), F32.stride(0)
+        d.Zh, d.ldz = ws["Zh"].data_ptr(), ws["Zh"].stride(0)
+        d.G, d.ldg = ws["dDh"].data_ptr(), ws["dDh"].stride(0)
+        d.partials, d.saved, d.sums = ws["hf_partials"].data_ptr(), ws["hf_saved"].data_ptr(), ws["hf_sums"].data_ptr()
+        d.acc = ws["acc"].data_ptr()
+        d.train, d.p_drop, d.momentum, d.eps = int(train), 0.1, MOMENTUM, EPS
+        d.seed_dev = a.step.data_ptr()
+        d.backward = int(backward)
+        for i, v in enumerate(self.vars):
+            mlp = model.MLPs[v]
+            hv = d.var[i]
+            hv.kind, hv.C, hv.slot = self.kinds[v], self.C[v], self.loss_names.index(v)
+            hv.W1, hv.b1 = a.p(f"MLPs.{v}.layer_1.weight"), a.p(f"MLPs.{v}.layer_1.bias")
+            hv.gamma, hv.beta = a.p(f"MLPs.{v}.batchnorm.weight"), a.p(f"MLPs.{v}.batchnorm.bias")
+            bn = mlp.batchnorm
+            hv.running_mean, hv.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            hv.num_batches_tracked = bn.num_batches_tracked.data_ptr()
+            hv.Wout = a.p(f"MLPs.{v}.layer_out.weight")
+            has_b = mlp.layer_out.bias is not None
+            hv.bout = a.p(f"MLPs.{v}.layer_out.bias") if has_b else None
+            hv.y = y[v].data_ptr() if (with_loss and y is not None) else None
+            hv.logits = ws["logits"][v].data_ptr()
+            mask = None if masks is None else masks.get(f"MLPs.{v}.dropout")
+            hv.mask, hv.ldm = (None, 0) if mask is None else (mask.data_ptr(), mask.stride(0))
+            hv.seed = eng.seed + 7919 * (i + 1)
+            hv.log_var = a.p(f"log_vars.{v}") if self.weighting else None
+            hv.dWout = a.g(f"MLPs.{v}.layer_out.weight")
+            hv.dbout = a.g(f"MLPs.{v}.layer_out.bias") if has_b else None
+            hv.dgamma, hv.dbeta = a.g(f"MLPs.{v}.batchnorm.weight"), a.g(f"MLPs.{v}.batchnorm.bias")
+        return d
+
     # ---- forward: F planes [B x L] (fp32 not needed) -> logits + loss accumulators ----
-    def forward(self, ws, Fp: Planes, B: int, y: Dict[str, torch.Tensor], train: bool, masks, with_loss: bool = True):
+    def forward(self, ws, Fp: Planes, B: int, y: Dict[str, torch.Tensor], train: bool, masks, with_loss: bool = True,
+                F32: Optional[torch.Tensor] = None, backward: bool = False, prezeroed: bool = False):
+        """F32: the fp32 matrix behind the planes Fp (enables the fused narrow-head path). backward: a backward pass
+        follows (the fused path then produces the head gradients in the same launch; `prezeroed` as in backward())."""
         eng, a = self.eng, self.eng.arena
         if not self.vars:
             return
         model = eng.model
+        ws["_fused"] = F32 is not None and self.fused()
+        if ws["_fused"]:
+            if backward and not prezeroed:
+                ws["hf_sums"].zero_()
+                for v in self.vars:
+                    a.view(f"MLPs.{v}.layer_out.weight", a.grad).zero_()
+                    if model.MLPs[v].layer_out.bias is not None:
+                        a.view(f"MLPs.{v}.layer_out.bias", a.grad).zero_()
+            ws["_F32"] = F32
+            L.heads_fwd(self._desc(ws, F32, B, y, train, masks, with_loss, backward and train))
+            return
         # the layer_1 biases as one concatenated vector: a single head whose width needs no padding reads its bias in
         # place; otherwise they are gathered (device-to-device copies of sh floats)
         if len(self.vars) == 1 and self.shp == self.sh:
@@ -367,6 +449,21 @@ class HeadsBlock:
         if not self.vars:
             return False
         model = eng.model
+        if ws.get("_fused"):
+            # fused path: heads_mid already produced G and the output-layer gradients; one launch finishes the section
+            d = self._desc(ws, ws["_F32"], B, y, True, masks, True, True)
+            d.dz_hi, d.dz_lo, d.ldzp = ws["dZh"].hi_ptr, ws["dZh"].lo_ptr, ws["dZh"].ld
+            if dF is not None:
+                d.df_hi, d.df_lo, d.ldfp = dF.hi_ptr, dF.lo_ptr, dF.ld
+            if dF_f32 is not None:
+                if accumulate:
+                    raise NotImplementedError("fused heads: accumulate into dF")
+                d.dF, d.lddf = dF_f32.data_ptr(), dF_f32.stride(0)
+            if dbias_ptr is not None:
+                d.dbias, d.zero_dbias = dbias_ptr, int(not prezeroed)
+            L.heads_bwd(d)
+            self._head_wgrads(ws, Fp, B, prezeroed, eng._mark())      # the weight gradients read the dZh planes written above
+            return True
         for i, v in enumerate(self.vars):
             mlp = model.MLPs[v]
             c0 = i * self.shp
@@ -396,13 +493,18 @@ class HeadsBlock:
                out=dF, colstats=dbias_ptr, stats_mode=3 if dbias_ptr is not None else 0, accumulate=accumulate,
                prezeroed=prezeroed)
 
+        self._head_wgrads(ws, Fp, B, prezeroed, ev)
+        return True
+
+    def _head_wgrads(self, ws, Fp: Planes, B: int, prezeroed: bool, ev):
+        eng, a = self.eng, self.eng.arena
+
         def wgrads():
             for i, v in enumerate(self.vars):      # dW1_v [sh x L] = dZh_v^T * F
                 dz = ws["dZh"].cols_view(i * self.shp, self.sh)
                 L.gemm(self.sh, self.L, B, dz, 1, Fp, 1, C_ptr=a.g(f"MLPs.{v}.layer_1.weight"), ldc=self.L, splitk=-1,
                        prezeroed=prezeroed)
         eng._aux_run(len(eng.aux) - 1, wgrads, after=ev)       # joined by the engine at the end of its backward pass
-        return True
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -590,7 +692,7 @@ class TrunkEngine(EngineBase):
         self._finish_init(self.n - 1)
         # stream-K fix-up workspaces of the first-layer GEMMs (one per modality branch: the branches overlap in time)
         self.fix = [L.FixWorkspace(self.device) for _ in range(self.n)]
-        self.wgrad_groups = split_groups([((self.h[i] + 255) // 256) * ((self.d[i] + 255) // 256) for i in range(self.n)])
+        self.wgrad_groups = split_groups_tiles([((self.h[i] + 255) // 256) * ((self.d[i] + 127) // 128) for i in range(self.n)])
 
     def wf_planes(self, i: Optional[int] = None) -> Planes:
         full = self.wplanes.planes(self.wf_off, self.latent, self.n * self.Lp, self.n * self.Lp)
@@ -624,7 +726,7 @@ class TrunkEngine(EngineBase):
         ws["dF"] = torch.zeros(R, self.Lp, device=dev)          # fp32 copy (triplet adds its own gradient here)
         ws["rowloss"] = torch.zeros(B, device=dev)
         ws["heads"] = self.heads.workspace(B)
-        ws["_zero"] = list(ws["sums"]) + [ws["heads"]["sums"]]     # accumulation scratch zeroed once per step
+        ws["_zero"] = list(ws["sums"]) + [ws["heads"]["sums"], ws["heads"]["hf_sums"]]   # accumulation scratch zeroed once per step
         self.ws[B] = ws
         return ws
 
@@ -755,7 +857,9 @@ class TrunkEngine(EngineBase):
         if pz:       # depends on the start of the step only, but is QUEUED behind the forward GEMMs so that they get the SMs first
             self._aux_run(zk, lambda: (self.arena.grad.zero_(), torch._foreach_zero_(ws["_zero"])), after=step_start)
         Fa = ws["F_p"].rows_view(0, B)
-        self.heads.forward(hw, Fa, B, y, True, masks)
+        if pz:       # the fused head kernels accumulate into the zeroed gradient arena during the forward pass already
+            self._aux_join(zk)
+        self.heads.forward(hw, Fa, B, y, True, masks, F32=ws["F"], backward=True, prezeroed=pz)
         if self.G == 3:
             Bp, Lp = ws["Bp"], self.Lp
             L.triplet_fwd(ws["F"].data_ptr(), fptr(ws["F"], Bp * Lp), fptr(ws["F"], 2 * Bp * Lp), Lp, B, self.latent, 1.0,
@@ -769,8 +873,6 @@ class TrunkEngine(EngineBase):
             dbias = a.g("encoders.0.layer_out.bias")
         else:
             dbias = None
-        if pz:
-            self._aux_join(zk)
         if self.G == 1:
             self.heads.backward(hw, Fa, B, y, masks, ws["dF_p"].rows_view(0, B), None, dbias, prezeroed=pz)
         else:
@@ -793,7 +895,7 @@ class TrunkEngine(EngineBase):
         hw["acc"].zero_()
         self.trunk_forward(ws, train_mode, masks)
         yl = self._labels(y) if y is not None else None
-        self.heads.forward(hw, ws["F_p"].rows_view(0, B), B, yl, train_mode, masks, with_loss=y is not None)
+        self.heads.forward(hw, ws["F_p"].rows_view(0, B), B, yl, train_mode, masks, with_loss=y is not None, F32=ws["F"])
         if y is not None:
             if self.G == 3:
                 Bp, Lp = ws["Bp"], self.Lp
@@ -989,7 +1091,7 @@ class VAEEngine(EngineBase):
                          dbias=a.g(f"{prefix}.hidden_layers.0.bias"), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
 
     # ---- forward: encoders -> latent -> decoders | heads | MMD ----
-    def _forward(self, ws, y, train: bool, noise, with_loss: bool, want_xhat: bool = False):
+    def _forward(self, ws, y, train: bool, noise, with_loss: bool, want_xhat: bool = False, backward: bool = False):
         a, hw = self.arena, ws["heads"]
         B, n, nd, Lt, Lp, P = ws["B"], self.ne, self.nd, self.latent, self.Lp, self.PRIOR
         noise = noise or {}
@@ -1024,7 +1126,7 @@ class VAEEngine(EngineBase):
         # ahead, the short chain runs on a few SMs while the GEMM's CTA pairs fill the others as they become free.
         self._fork()
         with torch.cuda.stream(self._aux_stream()):          # heads (incl. the single-CTA Cox sort, ~0.1 ms at B = 4096)
-            self.heads.forward(hw, ws["z_p"], B, y, train, noise, with_loss=with_loss)
+            self.heads.forward(hw, ws["z_p"], B, y, train, noise, with_loss=with_loss, F32=ws["z"], backward=backward)
         if with_loss:
             with torch.cuda.stream(self._mmd_stream()):      # Gram GEMMs of the MMD term: independent of the heads
                 self._mmd_forward(ws, train, noise)
@@ -1080,7 +1182,7 @@ class VAEEngine(EngineBase):
         y = self._labels(y)
         self.ensure_fresh()
         self.stage_inputs(ws, x_list, targets)
-        self._forward(ws, y, True, masks, True)
+        self._forward(ws, y, True, masks, True, backward=True)
         w_mmd = fptr(ws["wts"], self.mmd_slot)
         # ---- backward ----
         if not self.heads.backward(hw, ws["z_p"], B, y, masks, None, ws["dz"], None):
@@ -1244,7 +1346,7 @@ class GNNEngine(EngineBase):
     def _conv_inputs(self, ws):
         return [ws["x"]] + ws["D"]
 
-    def _forward(self, ws, y, train: bool, masks, with_loss: bool):
+    def _forward(self, ws, y, train: bool, masks, with_loss: bool, backward: bool = False):
         a, enc, hw = self.arena, self.model.encoders[0], ws["heads"]
         B, K, N, emb, Lt, Lp = ws["B"], self.K, self.N, self.emb, self.latent, self.Lp
         rows = B * N
@@ -1278,7 +1380,7 @@ class GNNEngine(EngineBase):
         L.gemm(B, Lt, N * emb, ws["Dlast_p"], 0, self.wp(self.wfc), 0, C_ptr=ws["E"].data_ptr(), ldc=Lp,
                bias=a.p("encoders.0.fc.bias"), splitk=-1)
         L.split_planes(ws["E"][:, :Lt], ws["E_p"])
-        self.heads.forward(hw, ws["E_p"], B, y, train, masks, with_loss=with_loss)
+        self.heads.forward(hw, ws["E_p"], B, y, train, masks, with_loss=with_loss, F32=ws["E"], backward=backward)
         if with_loss:
             self.heads.total(hw)
 
@@ -1298,7 +1400,7 @@ class GNNEngine(EngineBase):
         y = self._labels(y)
         self.ensure_fresh()
         self._stage(ws, x)
-        self._forward(ws, y, True, masks, True)
+        self._forward(ws, y, True, masks, True, backward=True)
         # ---- backward ----
         self.heads.backward(hw, ws["E_p"], B, y, masks, ws["dE_p"], None, a.g("encoders.0.fc.bias"))
         L.gemm(Lt, N * emb, B, ws["dE_p"], 1, ws["Dlast_p"], 1, C_ptr=a.g("encoders.0.fc.weight"), ldc=N * emb, splitk=-1)

@@ -191,6 +191,54 @@ int fxn_cox_max_rows(void);
  * d total / d loss_k. With weighting and n > 1, *dlog_vars[k] = 1 - exp(-s_k) * loss_k. Pointer tables are device arrays. */
 int fxn_total_loss(int n, const float* acc, const int* kinds, const float* const* log_vars, float* const* dlog_vars,
                    int weighting, float* out, void* stream);
+/* ---- the whole supervisor-head section in three launches (narrow heads: nv * pad8(sh) <= 64, C <= 16, MSE / CE) ----
+ * All target variables' MLPs (flexynesis/modules.py:135-150; the loop flexynesis/models/direct_pred.py:131-132) with
+ * their losses (direct_pred.py:146-190) and the autograd dual, on CUDA cores.
+ * fxn_heads_fwd: Zh = F W1cat^T + b1 -> BatchNorm1d (batch statistics merged from 16-row partials; running statistics
+ *   updated) -> ReLU -> Dropout(p_drop) -> layer_out -> logits; with labels: acc[slot] += (sum of row losses, valid
+ *   rows); with `backward`: G = d(weighted total loss)/d(BatchNorm output), sums += column sums of (G, G * xhat),
+ *   d layer_out.weight / bias accumulated (caller zeroes sums and those gradients).
+ * fxn_heads_bwd: dZh = gamma rstd (G - mean G - xhat mean(G xhat)) -> planes (dz_hi, dz_lo) for the layer_1 weight
+ *   gradient; dF = dZh W1cat -> planes (df_hi, df_lo), optional fp32 dF, dbias[L] += column sums of dF (caller zeroes);
+ *   d gamma / d beta written. */
+#define FXN_HEADS_MAX_VARS 8
+typedef struct fxn_heads_var {
+  int kind;                 /* 1 MSE over rows with non-NaN y, 2 cross-entropy over rows with y != -1 and non-NaN */
+  int C;                    /* outputs of layer_out */
+  int slot;                 /* row of the loss table */
+  const float* W1; const float* b1;                     /* layer_1 [sh x L], [sh] */
+  const float* gamma; const float* beta;                /* batchnorm affine [sh] */
+  float* running_mean; float* running_var; void* num_batches_tracked;
+  const float* Wout; const float* bout;                 /* layer_out [C x sh], [C] or NULL */
+  const float* y;                                       /* labels [B] or NULL (no loss for this variable) */
+  float* logits;                                        /* [B x C] */
+  const uint8_t* mask; long long ldm;                   /* optional explicit dropout keep mask [B x sh] */
+  unsigned long long seed;                              /* Philox seed of this head's dropout */
+  const float* log_var;                                 /* device scalar s_k: loss weight exp(-s_k); NULL = 1 */
+  float* dWout; float* dbout; float* dgamma; float* dbeta;
+} fxn_heads_var;
+typedef struct fxn_heads_desc {
+  int B, L, sh, nv;
+  const float* F; long long ldf;            /* input of the heads (fused embedding), fp32 [B x L] */
+  float* Zh; long long ldz;                 /* [B x nv * pad8(sh)] layer_1 outputs, kept for the backward pass */
+  float* G; long long ldg;                  /* same shape */
+  float* partials;                          /* [2][nv * pad8(sh)][ceil(B / 16) rounded up to 32] */
+  float* saved;                             /* [2][nv * pad8(sh)] mean, rstd */
+  float* sums;                              /* [2][nv * pad8(sh)] */
+  float* acc;                               /* loss table [n][2] (caller zeroes) */
+  int train; float p_drop; float momentum; float eps;
+  const void* seed_dev;                     /* optional device int64 mixed into the dropout seeds (per-step counter) */
+  int backward;
+  fxn_heads_var var[FXN_HEADS_MAX_VARS];
+  void* dz_hi; void* dz_lo; long long ldzp;
+  void* df_hi; void* df_lo; long long ldfp;
+  float* dF; long long lddf;
+  float* dbias; int zero_dbias;             /* zero_dbias != 0: the call clears dbias[L] first */
+} fxn_heads_desc;
+int fxn_heads_fused_ok(int L, int sh, int nv, int maxC);
+int fxn_heads_fwd(const fxn_heads_desc* d, void* stream);
+int fxn_heads_bwd(const fxn_heads_desc* d, void* stream);
+
 /* triplet_loss (triplet_encoder.py:178-194): mean_b relu(|a-p|^2 - |a-n|^2 + margin); acc as above. */
 int fxn_triplet_fwd(const float* A, const float* P, const float* N, long long ld, int rows, int L, float margin,
                     float* rowloss, float* acc, void* stream);

@@ -166,7 +166,12 @@ def test_gemm_planner_invariants():
     assert L.gemm_plan(4096, 512, 5000, 3, 0, False, 256)["block_n"] == 256
     assert L.gemm_plan(4096, 307, 3000, 3, 0, False, 160)["block_n"] == 160
     big = L.gemm_plan(512, 5000, 4096, 3, 1, True, 0)                 # config-2 weight gradient: stream-K over every SM
-    assert big["streamk"] == 1 and big["groups"] == 74 and big["block_n"] == 256
+    assert big["streamk"] == 1 and big["groups"] == 74 and big["block_n"] in (128, 256)
+    capped = L.gemm_plan(512, 5000, 4096, 3, 1, True, 0, max_groups=40)    # the engine splits the chip between two wgrads
+    assert capped["groups"] == 40                                          # (80 tiles on 40 pairs: two whole rounds, no split tile)
+    fix = L.gemm_plan(4096, 1024, 24000, 3, 0, False, 0, fix=True)         # config 5 forward: 64 tiles over all 74 pairs
+    assert fix["streamk"] == 2 and fix["groups"] == 74
+    assert L.gemm_plan(4096, 256, 512, 3, 0, False, 0, fix=True)["streamk"] == 0   # short K: whole tiles
 
 
 def _golden(name):
