@@ -148,7 +148,13 @@ def build_model(w, prob, dev):
         model = fx.GNN(cfg, prob["view"], targets, gnn_conv_type="GCN", **kw)
     else:
         model = getattr(fx, w["model"])(cfg, prob["view"], targets, **kw)
-    return model.to(dev).train()
+    return model.to(dev).train() if dev is not None else model
+
+
+def count_params(w) -> int:
+    """Trainable parameters of the workload's model (the drop-in class built on the host; same number in both arms)."""
+    small = dict(w, B=min(w["B"], 64))
+    return int(sum(p.numel() for p in build_model(w, build_problem(small, 0), None).parameters()))
 
 
 def device_batch(prob, dev):
@@ -287,12 +293,22 @@ def run_reference(args, w):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sps, per_step, done = cpu_reference_steps(w, args.steps, min(args.warmup, 3), threads, budget_s=120.0)
+    warm = max(args.warmup, 3)
+    sps, per_step, done = cpu_reference_steps(w, args.steps, warm, threads, budget_s=150.0)
+    try:
+        nparams = count_params(w)
+    except Exception:
+        nparams = None
     line = {
         "impl": "reference", "metric": "train_samples_per_sec", "value": sps, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 3), "ms_per_step": per_step * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "steps_completed": done, "warmup": warm, "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["describe"], "batch": w["B"], "name": args.workload},
+        # same workload keys as the b200 arm (the CPU arm always runs ONE replica of the per-GPU batch on the host cores)
+        "config": {"workload": w["describe"], "name": args.workload, "batch_per_gpu": w["B"], "global_batch": w["B"] * args.gpus,
+                   "params": nparams, "parallelism": f"dp{args.gpus}"},
+        "details": {"note": "oracle port of the reference's torch CPU training step (faster than the real reference: "
+                            "vectorised dropout draws, Gram-form MMD); ONE host process with all cores runs one replica of "
+                            "the per-GPU batch whatever --gpus says; stops early at 150 s of timed work"},
         "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "cpu": cpu_model_name(),
                          "sample": f"{done} full-batch steps (B={w['B']}) after warm-up, pre-collated batch; oracle port "
                                    "of the reference's torch CPU path (real Lightning is not installable offline)"},
@@ -311,12 +327,11 @@ def measured_traffic(workload: str):
         return None
 
 
-def roofline_gemm(model, w, dev):
+def roofline_gemm(model, w, dev, ws):
     """Encoder-0 first-layer GEMM (the largest contraction of the step) timed alone, L2 flushed between launches."""
     from flexynesis_b200 import _lib as L
     eng = model.engine()
     B = w["B"]
-    ws = eng.ws[B]
     M, N, K = B, eng.h[0], eng.d[0]
     if w["model"] == "supervised_vae":
         out, bias, epi = ws["A"][0], eng.arena.p("encoders.0.hidden_layers.0.bias"), 6
@@ -374,12 +389,11 @@ def roofline_gemm(model, w, dev):
             "ncu": {k: ev.get(k) for k in ("tensor_pipe_active_pct", "duration_us_under_ncu", "source")} if ev else None}
 
 
-def roofline_gcn(model, w, dev):
+def roofline_gcn(model, w, dev, ws):
     """Second GCN layer forward (reads [B,N,32], writes [B,N,32]) timed alone: HBM-bound."""
     from flexynesis_b200 import _lib as L
     eng = model.engine()
     B = w["B"]
-    ws = eng.ws[B]
     N, emb = eng.N, eng.emb
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     evs = []
@@ -412,6 +426,181 @@ def roofline_gcn(model, w, dev):
             "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes": nbytes, "traffic": measured_traffic(w.get("name", ""))}
 
 
+def timed_replays(step, steps: int, world: int, dev):
+    """ms per step of `steps` graph replays: CUDA events on the launching stream, barrier + synchronize on both sides, max
+    over ranks."""
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t) / steps
+
+
+def build_data_parallel(w, prob, dev, world, use_nccl):
+    """(model, allreduce, mode, note) for this rank: NVSwitch-multicast step when available, NCCL otherwise (announced)."""
+    import torch.distributed as dist
+    from flexynesis_b200.parallel import GradAllReduce, NvlsDataParallel
+    if world > 1 and not use_nccl and NvlsDataParallel.available():
+        with NvlsDataParallel.arena_allocation():
+            model = build_model(w, prob, dev)
+            eng = model.engine(dev)
+        try:
+            allreduce, ok, note = NvlsDataParallel(eng), 1, ""
+        except Exception as e:                         # no multicast support on this box: say so, use NCCL
+            allreduce, ok, note = None, 0, f"NVLS unavailable ({type(e).__name__}: {e})"[:200]
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) == 1:
+            return model, allreduce, "nvls", note
+        return model, GradAllReduce(world), "nccl", note
+    model = build_model(w, prob, dev)
+    return model, (GradAllReduce(world) if world > 1 else None), ("nccl" if world > 1 else "single"), ""
+
+
+def dp_consistency(model, allreduce, world, dev):
+    """After the timed steps: (1) every rank holds bit-identical parameters; (2) ONE more optimizer step through the
+    multicast kernels equals the same step through an NCCL all-reduce + the single-GPU optimizer kernel (same gradients,
+    same Adam state) to fp32 rounding."""
+    import torch.distributed as dist
+    eng = model.engine(dev)
+    a = eng.arena
+    torch.cuda.synchronize()
+    dist.barrier()
+    mine = a.flat.double()
+    chk = torch.stack([mine.sum(), (mine * mine).sum(), mine.abs().max()])
+    allchk = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allchk, chk)
+    identical = all(bool(torch.equal(c, allchk[0])) for c in allchk)
+    rec = {"params_identical_across_ranks": identical, "ranks": world}
+    if hasattr(allreduce, "step"):
+        g = torch.Generator(device=dev).manual_seed(1234 + dist.get_rank())
+        grad = torch.randn(a.numel, device=dev, generator=g) * 1e-2
+        state = [t.clone() for t in (a.flat, a.exp_avg, a.exp_avg_sq, a.step)]
+        a.grad.copy_(grad)
+        torch.cuda.synchronize(); dist.barrier()
+        allreduce.step(1e-3)
+        torch.cuda.synchronize(); dist.barrier()
+        got = a.flat.clone()
+        for dst, src in zip((a.flat, a.exp_avg, a.exp_avg_sq, a.step), state):
+            dst.copy_(src)
+        torch.cuda.synchronize(); dist.barrier()
+        ref_grad = grad.clone()
+        dist.all_reduce(ref_grad)
+        a.grad.copy_(ref_grad)
+        eng.optimizer_step(1e-3, 1.0, 1.0 / world)
+        torch.cuda.synchronize()
+        diff = float((a.flat - got).abs().max())
+        scale = float((a.flat - state[0]).abs().max())
+        t = torch.tensor([diff], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rec.update({"multicast_step_vs_nccl_step_max_abs_diff": float(t), "update_scale": scale})
+        for dst, src in zip((a.flat, a.exp_avg, a.exp_avg_sq, a.step), state):
+            dst.copy_(src)
+        eng.wplanes.refresh()
+        torch.cuda.synchronize(); dist.barrier()
+    return rec
+
+
+def secondary_workload(name, args, world, rank, local, dev):
+    """value / ms_per_step of another BASELINE config at this GPU count (device-resident graph replays, same protocol)."""
+    from flexynesis_b200.fit import GraphedStep
+    w2 = WORKLOADS[name]
+    prob = build_problem(w2, rank)
+    model, allreduce, mode, _ = build_data_parallel(w2, prob, dev, world, args.nccl)
+    model.engine(dev).seed += 7919 * rank
+    step = GraphedStep(model, device_batch(prob, dev), allreduce=allreduce, grad_scale=1.0 / world)
+    for _ in range(3):
+        step()
+    n = max(10, args.steps // 2)
+    ms = timed_replays(step, n, world, dev)
+    rec = {"workload": w2["describe"], "value": world * w2["B"] / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+           "steps": n, "batch_per_gpu": w2["B"], "data_parallel": mode,
+           "model_tflops": train_flops_per_sample(w2) * world * w2["B"] / (ms * 1e-3) / 1e12}
+    del step, model
+    torch.cuda.empty_cache()
+    return rec
+
+
+def minibatch_records(w, dev):
+    """The reference's default regime (B <= 128, flexynesis/main.py:183-190) on one GPU: (a) fit()'s CUDA-graphed
+    mini-batch step fed by the device batcher, (b) the Lightning-shaped loop a flexynesis user gets when the drop-in class
+    is handed to pl.Trainer: training_step -> backward -> clip_grad_norm_ -> torch Adam (main.py:212-225), eager."""
+    import flexynesis_b200 as fx
+    from flexynesis_b200.data import DeviceBatcher
+    from flexynesis_b200.fit import GraphedStep
+    out = {}
+    B = 128
+    vt = {v: VT[v] for v in w["vars"]}
+    ds = fx.SyntheticMultiOmicDataset(w["dims"], 2048, vt, w["classes"], seed=0)
+    view = _View()
+    view.dat, view.features, view.variable_types, view.ann = ds.dat, ds.features, ds.variable_types, ds.clean_ann()
+    prob = dict(view=view)
+    model = build_model(w, prob, dev)
+    loader = DeviceBatcher(ds, B, dev, shuffle=True, drop_last=True, seed=0)
+    graphed = None
+    def epoch():
+        nonlocal graphed
+        for batch in loader:
+            if graphed is None:
+                graphed = GraphedStep(model, batch, resplit_inputs=True)
+            graphed()
+    epoch(); epoch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n_ep = 8
+    for _ in range(n_ep):
+        epoch()
+    e1.record()
+    torch.cuda.synchronize()
+    steps = n_ep * len(loader)
+    ms = e0.elapsed_time(e1) / steps
+    out["graphed_fit_B128"] = {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "steps": steps,
+                               "includes": "device permutation gather of every batch + captured step (re-split, fwd, bwd, "
+                                           "clip, Adam, plane refresh)"}
+    # (b) Lightning-shaped loop, eager, torch optimizer on the arena-backed parameters
+    for Bl in (128, w["B"]):
+        dsl = fx.SyntheticMultiOmicDataset(w["dims"], Bl, vt, w["classes"], seed=1)
+        viewl = _View()
+        viewl.dat, viewl.features, viewl.variable_types, viewl.ann = dsl.dat, dsl.features, dsl.variable_types, dsl.clean_ann()
+        m = build_model(w, dict(view=viewl), dev)
+        opt = m.configure_optimizers()
+        batch = ({k: v.to(dev) for k, v in dsl.dat.items()}, {k: v.to(dev) for k, v in dsl.ann.items()}, None)
+        def lstep():
+            opt.zero_grad(set_to_none=True)
+            loss = m.training_step(batch, 0, log=False)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            opt.step()
+        for _ in range(5):
+            lstep()
+        torch.cuda.synchronize()
+        n = 40 if Bl <= 128 else 20
+        t0 = time.perf_counter()
+        for _ in range(n):
+            lstep()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n
+        out[f"lightning_loop_B{Bl}"] = {"value": Bl / dt, "unit": "samples/s", "ms_per_step": dt * 1e3, "steps": n,
+                                        "includes": "eager training_step (engine forward + backward), autograd hand-over of the "
+                                                    "engine's gradients, torch clip_grad_norm_, torch Adam.step, plane refresh "
+                                                    "on the next forward; host wall clock"}
+        del m, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args, w):
     import torch.distributed as dist
     from flexynesis_b200 import _lib as L
@@ -429,27 +618,8 @@ def run_b200(args, w):
         dist.init_process_group("nccl", device_id=dev)
     B = w["B"]
     prob = build_problem(w, rank)                      # this rank's shard of the sample-sharded dataset
-    dp_mode, dp_note = "single", ""
-    if world > 1 and not args.nccl and NvlsDataParallel.available():
-        # arenas in symmetric memory; gradient reduce-scatter / Adam / parameter all-gather through NVSwitch multicast
-        with NvlsDataParallel.arena_allocation():
-            model = build_model(w, prob, dev)
-            eng = model.engine(dev)
-        try:
-            allreduce = NvlsDataParallel(eng)
-            ok = 1
-        except Exception as e:                         # no multicast support on this box: say so, use NCCL
-            allreduce, ok, dp_note = None, 0, f"NVLS unavailable ({type(e).__name__}: {e})"[:200]
-        flag = torch.tensor([ok], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag) == 1:
-            dp_mode = "nvls"
-        else:
-            allreduce, dp_mode = GradAllReduce(world), "nccl"
-    else:
-        model = build_model(w, prob, dev)
-        allreduce = GradAllReduce(world) if world > 1 else None
-        dp_mode = "nccl" if world > 1 else "single"
+    # N > 1: arenas in symmetric memory; gradient reduce-scatter / Adam / parameter all-gather through NVSwitch multicast
+    model, allreduce, dp_mode, dp_note = build_data_parallel(w, prob, dev, world, args.nccl)
     model.engine(dev).seed += 7919 * rank              # different dropout streams on different shards
     nparams = sum(p.numel() for p in model.parameters())
 
@@ -457,27 +627,13 @@ def run_b200(args, w):
     batch = device_batch(prob, dev)
     step = GraphedStep(model, batch, allreduce=allreduce, grad_scale=1.0 / world)
     warm = max(args.warmup, 3)
-    for _ in range(warm):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
+        time.sleep(0.5)                                # nvidia-smi needs a moment before its first sample
+    for _ in range(warm):
         step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t) / args.steps
+    ms_per_step = timed_replays(step, args.steps, world, dev)
     clocks = sampler.stop() if rank == 0 else None
     value = world * B / (ms_per_step * 1e-3)
     launches = step.launches_per_step * args.steps
@@ -517,11 +673,34 @@ def run_b200(args, w):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(dt)
 
+    # ---------------- sustained record: the same replay for >= 3 s with its own clock / power samples ----------------
+    sustained = None
+    if not args.quick:
+        n_sus = max(args.steps, int(3000.0 / ms_per_step))
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+        ms_sus = timed_replays(step, n_sus, world, dev)
+        sustained = {"value": world * B / (ms_sus * 1e-3), "unit": "samples/s", "ms_per_step": ms_sus, "steps": n_sus,
+                     "seconds": n_sus * ms_sus * 1e-3, "clocks": sampler2.stop() if rank == 0 else None}
+    # ---------------- data-parallel consistency (N > 1) ----------------
+    dp_check = dp_consistency(model, allreduce, world, dev) if world > 1 else None
+    # ---------------- other BASELINE configs at this GPU count + the reference's default mini-batch regime ----------------
+    also = {}
+    if not args.quick:
+        if args.workload != "cfg5":
+            also["cfg5"] = secondary_workload("cfg5", args, world, rank, local, dev)
+        if world == 1 and w["model"] == "DirectPred":
+            try:
+                also.update(minibatch_records(w, dev))
+            except Exception as e:                      # never lose the bench line over a secondary record
+                also["minibatch_error"] = f"{type(e).__name__}: {e}"[:200]
+
     # ---------------- roofline of the dominant kernel + CPU baseline (rank 0) ----------------
     roofline = cpu_base = None
     if rank == 0:
         w = dict(w, name=args.workload)
-        roofline = roofline_gcn(model, w, dev) if w["model"] == "GNN" else roofline_gemm(model, w, dev)
+        roofline = roofline_gcn(model, w, dev, step.ws) if w["model"] == "GNN" else roofline_gemm(model, w, dev, step.ws)
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             sps, per, done = cpu_reference_steps(w, 20, 2, threads, budget_s=25.0)
@@ -547,8 +726,8 @@ def run_b200(args, w):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split tcgen05, fp32 accumulate)",
             "data": "synthetic",
             "config": {"workload": w["describe"], "name": args.workload, "batch_per_gpu": B,
-                       "global_batch": B * world, "params": nparams, "parallelism": f"dp{world}",
-                       "l2_policy": "inputs larger than L2: the operand planes one step streams (131 MB for cfg2) exceed "
+                       "global_batch": B * world, "params": nparams, "parallelism": f"dp{world}"},
+            "details": {"l2_policy": "inputs larger than L2: the operand planes one step streams (131 MB for cfg2) exceed "
                                     "the 126 MB L2; the roofline kernel is timed with an explicit 256 MB L2 flush",
                        "input_prep": "value: planes of the resident full batch are split once and reused; e2e: every step's "
                                      "batch is copied from pinned host memory (double-buffered, overlapped with the previous "
@@ -556,13 +735,15 @@ def run_b200(args, w):
                        "step": "CUDA-graph replay of fwd+bwd+clip+Adam+plane refresh" + {
                            "single": "",
                            "nccl": "; NCCL all-reduce of the flat gradient arena between the backward and optimizer graphs",
-                           "nvls": "; gradients reduce-scattered by multimem.ld_reduce, Adam on a 1/W slice per rank, "
-                                   "parameters all-gathered by multimem.st (NVSwitch multicast, csrc/dp.cu)"}[dp_mode],
+                           "nvls": "; in the same graph: gradients reduce-scattered by multimem.ld_reduce, Adam on a 1/W slice "
+                                   "per rank, parameters all-gathered by multimem.st, three in-stream multimem barriers "
+                                   "(NVSwitch multicast, csrc/dp.cu)"}[dp_mode],
                        "data_parallel": dp_mode, "data_parallel_note": dp_note},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
             "gpu_launches": launches, "launches_per_step": step.launches_per_step,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base,
+            "clocks": clocks, "sustained": sustained, "dp_check": dp_check, "also": also,
+            "roofline": roofline, "cpu_baseline": cpu_base,
             "model_tflops": fl * value / 1e12, "final_loss": final_loss,
         }
         emit(line)
@@ -593,6 +774,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--nccl", action="store_true", help="multi-GPU: NCCL all-reduce instead of the NVSwitch multicast step")
     ap.add_argument("--profile", action="store_true", help="timed steps only (for ncu launch lists): no e2e/roofline/cpu legs")
+    ap.add_argument("--quick", action="store_true", help="skip the sustained / other-config / mini-batch sub-records")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     # stdout carries exactly ONE JSON line: file descriptor 1 is pointed at stderr for the life of the process (NCCL prints

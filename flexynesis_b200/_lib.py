@@ -121,7 +121,7 @@ SYMBOLS = [
     "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_heads_fused_ok", "fxn_heads_fwd", "fxn_heads_bwd", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
     "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn", "fxn_gcn_fwd", "fxn_gcn_bwd",
-    "fxn_merge_col_stats", "fxn_node_lin_fwd", "fxn_node_lin_bwd", "fxn_debug_gemm_trace", "fxn_debug_gemm_cta_times", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast",
+    "fxn_merge_col_stats", "fxn_node_lin_fwd", "fxn_node_lin_bwd", "fxn_debug_gemm_trace", "fxn_debug_gemm_cta_times", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast", "fxn_dp_barrier",
 ]
 
 
@@ -434,3 +434,8 @@ def dp_adam_bcast(mc_param, param_local, grad_local, m, v, begin, end, partials,
                                 C.c_void_p(v), c_ll(begin), c_ll(end), C.c_void_p(partials), C.c_int(world), C.c_float(lr),
                                 C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(max_norm), C.c_void_p(step),
                                 C.c_void_p(norm_out), C.c_void_p(stream())), "fxn_dp_adam_bcast")
+
+
+def dp_barrier(mc_flags, local_flags, epoch, slot, world) -> None:
+    check(lib.fxn_dp_barrier(C.c_void_p(mc_flags), C.c_void_p(local_flags), C.c_void_p(epoch), C.c_int(slot), C.c_int(world),
+                             C.c_void_p(stream())), "fxn_dp_barrier")

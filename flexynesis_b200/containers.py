@@ -95,11 +95,11 @@ class GCNConv(nn.Module):
 
     @staticmethod
     def normalized_edges(edge_index: torch.Tensor, num_nodes: int):
+        # torch_geometric's add_remaining_self_loops: input self loops are dropped, then ONE unit loop per node is appended
         src, dst = edge_index[0].long(), edge_index[1].long()
-        looped = torch.zeros(num_nodes, dtype=torch.bool, device=edge_index.device)
-        looped[src[src == dst]] = True
-        extra = torch.nonzero(~looped).flatten()
-        src, dst = torch.cat([src, extra]), torch.cat([dst, extra])
+        keep = src != dst
+        loops = torch.arange(num_nodes, device=edge_index.device)
+        src, dst = torch.cat([src[keep], loops]), torch.cat([dst[keep], loops])
         deg = torch.zeros(num_nodes, device=edge_index.device).scatter_add_(0, dst, torch.ones_like(dst, dtype=torch.float32))
         dinv = deg.pow(-0.5)
         dinv[torch.isinf(dinv)] = 0

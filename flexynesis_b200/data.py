@@ -71,8 +71,10 @@ class DeviceBatcher:
         self.gen = torch.Generator(device=self.device).manual_seed(seed)
         self.full_batch = batch_size >= self.n
         self._tag = 0
+        # static batch buffers (features and labels): a captured training step reads them in place, batch after batch
         self._out = {k: torch.empty(batch_size, v.shape[1], device=self.device) for k, v in self.dat.items()} \
             if not self.full_batch else None
+        self._yout = {k: torch.empty(batch_size, device=self.device) for k in self.ann} if not self.full_batch else None
 
     def __len__(self):
         if self.full_batch:
@@ -98,7 +100,54 @@ class DeviceBatcher:
                 self._tag += 1
                 out._fxn_tag = self._tag   # written through a raw pointer: tell the engine's plane cache it changed
                 dat[k] = out
-            yield dat, {k: v[idx] for k, v in self.ann.items()}, None
+            yy = {}
+            for k, v in self.ann.items():
+                yy[k] = torch.index_select(v, 0, idx, out=self._yout[k][:rows])
+            yield dat, yy, None
+
+
+class DeviceNodeBatcher:
+    """Batches for the GNN from the reference's MultiOmicDatasetNW duck type (flexynesis/data.py:1154-1262):
+    `node_features_tensor` [samples, nodes, features] and `ann` stay resident in HBM; a batch is one row gather over
+    the [samples, nodes * features] view. Yields (x [B, nodes, features], y_dict, None) like default_collate over
+    MultiOmicDatasetNW.__getitem__ (:1257-1262)."""
+
+    def __init__(self, dataset, batch_size: int, device, shuffle: bool = True, drop_last: bool = True, seed: int = 0):
+        self.device = torch.device(device)
+        x = torch.as_tensor(dataset.node_features_tensor).to(self.device, torch.float32).contiguous()
+        self.shape = tuple(x.shape[1:])
+        self.x = x.view(x.shape[0], -1)
+        self.ann = {k: torch.as_tensor(v).to(self.device, torch.float32).contiguous() for k, v in dataset.ann.items()}
+        self.n = int(x.shape[0])
+        self.batch_size, self.shuffle, self.drop_last = batch_size, shuffle, drop_last
+        self.gen = torch.Generator(device=self.device).manual_seed(seed)
+        self.full_batch = batch_size >= self.n
+        self._tag = 0
+        self._out = None if self.full_batch else torch.empty(batch_size, self.x.shape[1], device=self.device)
+        self._yout = None if self.full_batch else {k: torch.empty(batch_size, device=self.device) for k in self.ann}
+
+    def __len__(self):
+        if self.full_batch:
+            return 1
+        return self.n // self.batch_size if self.drop_last else -(-self.n // self.batch_size)
+
+    def __iter__(self):
+        if self.full_batch:
+            yield self.x.view(self.n, *self.shape), self.ann, None
+            return
+        perm = torch.randperm(self.n, device=self.device, generator=self.gen) if self.shuffle \
+            else torch.arange(self.n, device=self.device)
+        for b in range(len(self)):
+            idx = perm[b * self.batch_size:(b + 1) * self.batch_size].contiguous()
+            rows = idx.numel()
+            out = self._out[:rows]
+            L.gather_rows(self.x.data_ptr(), self.x.stride(0), idx.data_ptr(), rows, self.x.shape[1], out.data_ptr(),
+                          out.stride(0))
+            self._tag += 1
+            xb = out.view(rows, *self.shape)
+            xb._fxn_tag = self._tag
+            yy = {k: torch.index_select(v, 0, idx, out=self._yout[k][:rows]) for k, v in self.ann.items()}
+            yield xb, yy, None
 
 
 class DeviceTripletBatcher:
@@ -138,6 +187,7 @@ class DeviceTripletBatcher:
         self.valid = torch.nonzero(~nan).flatten().to(dev)
         self.gen = torch.Generator(device=dev).manual_seed(seed)
         self._buf = [{k: torch.empty(batch_size, v.shape[1], device=dev) for k, v in self.dat.items()} for _ in range(3)]
+        self._ybuf = {k: torch.empty(batch_size, device=dev) for k in self.ann}
         self._tag = 0
 
     def __len__(self):
@@ -176,4 +226,5 @@ class DeviceTripletBatcher:
         for b in range(len(self)):
             a = perm[b * self.batch_size:(b + 1) * self.batch_size]
             p, q = self.sample_indices(a)
-            yield self._gather(0, a), self._gather(1, p), self._gather(2, q), {k: v[a] for k, v in self.ann.items()}
+            yy = {k: torch.index_select(v, 0, a, out=self._ybuf[k][:a.numel()]) for k, v in self.ann.items()}
+            yield self._gather(0, a), self._gather(1, p), self._gather(2, q), yy

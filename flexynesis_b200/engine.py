@@ -327,7 +327,7 @@ class HeadsBlock:
         d.partials, d.saved, d.sums = ws["hf_partials"].data_ptr(), ws["hf_saved"].data_ptr(), ws["hf_sums"].data_ptr()
         d.acc = ws["acc"].data_ptr()
         d.train, d.p_drop, d.momentum, d.eps = int(train), 0.1, MOMENTUM, EPS
-        d.seed_dev = a.step.data_ptr()
+        d.seed_dev = eng.noise_step.data_ptr()
         d.backward = int(backward)
         for i, v in enumerate(self.vars):
             mlp = model.MLPs[v]
@@ -392,7 +392,7 @@ class HeadsBlock:
                      gamma=a.p(f"MLPs.{v}.batchnorm.weight"), beta=a.p(f"MLPs.{v}.batchnorm.bias"),
                      momentum=MOMENTUM, eps=EPS, train=int(train), act=1, p_drop=0.1 if train else 0.0,
                      mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
-                     seed=eng.seed + 7919 * (i + 1), seed_dev=eng.arena.step.data_ptr(),
+                     seed=eng.seed + 7919 * (i + 1), seed_dev=eng.noise_step.data_ptr(),
                      out=fptr(ws["Dh"], c0), ldo=ws["Dh"].stride(0), saved=ws["saved"][i].data_ptr(),
                      **_bn_ptrs(mlp.batchnorm))
             bias = a.p(f"MLPs.{v}.layer_out.bias") if mlp.layer_out.bias is not None else None
@@ -482,7 +482,7 @@ class HeadsBlock:
                             ldg=ws["dDh"].stride(0), rows=B, cols=self.sh, gamma=a.p(f"MLPs.{v}.batchnorm.weight"),
                             beta=a.p(f"MLPs.{v}.batchnorm.bias"), saved=ws["saved"][i].data_ptr(), act=1, p_drop=0.1,
                             mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
-                            seed=eng.seed + 7919 * (i + 1), seed_dev=eng.arena.step.data_ptr(), pre_act=0,
+                            seed=eng.seed + 7919 * (i + 1), seed_dev=eng.noise_step.data_ptr(), pre_act=0,
                             sums=ws["sums"][i], dgamma=a.view(f"MLPs.{v}.batchnorm.weight", a.grad),
                             dbeta=a.view(f"MLPs.{v}.batchnorm.bias", a.grad), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld,
                             prezeroed=prezeroed)
@@ -503,7 +503,7 @@ class HeadsBlock:
             for i, v in enumerate(self.vars):      # dW1_v [sh x L] = dZh_v^T * F
                 dz = ws["dZh"].cols_view(i * self.shp, self.sh)
                 L.gemm(self.sh, self.L, B, dz, 1, Fp, 1, C_ptr=a.g(f"MLPs.{v}.layer_1.weight"), ldc=self.L, splitk=-1,
-                       prezeroed=prezeroed)
+                       prezeroed=prezeroed, max_groups=eng.aux_groups)
         eng._aux_run(len(eng.aux) - 1, wgrads, after=ev)       # joined by the engine at the end of its backward pass
 
 
@@ -516,17 +516,33 @@ class EngineBase:
 
     def __init__(self, model, device, extra_losses: Sequence = ()):
         self.model, self.device = model, torch.device(device)
-        self.seed = 0x5EED
+        # Noise of this engine (dropout masks, the VAE's epsilon and MMD prior draws): Philox keyed by (seed, noise counter,
+        # element). The seed follows torch's global seed at engine creation (torch.manual_seed / seed_everything give each
+        # model / HPO trial its own stream); the counter lives on the device and advances once per forward pass, inside
+        # captured graphs too, independently of who runs the optimizer (a Lightning loop stepping a torch optimizer never
+        # touches the Adam step counter the noise used to be keyed by).
+        self.seed = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + 0x5EED) & 0x7FFFFFFFFFFFFFFF
+        self.noise_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.arena = ParamArena(model, self.device)
         self.wplanes = WeightPlanes(self.arena)
         self.latent = int(model.config["latent_dim"])
         self.Lp = pad8(self.latent)
         self._extra_losses = extra_losses
         self.inputs = InputCache()
-        self.ws: Dict[int, dict] = {}
+        self.ws: Dict[object, dict] = {}
+        self.ws_tag = ""          # non-empty while a GraphedStep warms up / captures: that graph gets a private workspace
         self.side: List[torch.cuda.Stream] = []
         self.parallel_encoders = True
+        # SM pairs an off-critical-path weight gradient may occupy (they run beside the dgrad -> BatchNorm -> dgrad chain;
+        # uncapped, each stream-K launch took all 74 pairs and the chain's kernels queued behind them)
+        self.aux_groups = int(__import__("os").environ.get("FXN_AUX_GROUPS", "12"))
         self.sync = None          # parallel.GlobalBatchSync: N ranks reproduce one step on the concatenated batch
+
+    def _ws_key(self, B: int):
+        """Workspaces (activations, operand planes of the staged inputs) are keyed by batch size, plus the tag of the
+        captured graph that owns them: a replayed graph reads its input planes without re-splitting them, so an eager call
+        with the same batch size (validation, predict) must never stage other data into the graph's buffers."""
+        return B if not self.ws_tag else (B, self.ws_tag)
 
     def _finish_init(self, n_side: int):
         """Call at the end of a subclass constructor, after every weight plane has been registered."""
@@ -699,8 +715,9 @@ class TrunkEngine(EngineBase):
         return full if i is None else full.cols_view(i * self.Lp, self.latent)
 
     def workspace(self, B: int) -> dict:
-        if B in self.ws:
-            return self.ws[B]
+        key = self._ws_key(B)
+        if key in self.ws:
+            return self.ws[key]
         dev, G = self.device, self.G
         Bp = B if G == 1 else pad128(B)
         R = G * Bp
@@ -727,7 +744,7 @@ class TrunkEngine(EngineBase):
         ws["rowloss"] = torch.zeros(B, device=dev)
         ws["heads"] = self.heads.workspace(B)
         ws["_zero"] = list(ws["sums"]) + [ws["heads"]["sums"], ws["heads"]["hf_sums"]]   # accumulation scratch zeroed once per step
-        self.ws[B] = ws
+        self.ws[key] = ws
         return ws
 
     # -- input staging --
@@ -738,7 +755,7 @@ class TrunkEngine(EngineBase):
                     x = x.to(self.device, torch.float32)
                 x = x.contiguous() if x.stride(-1) != 1 else x
                 dst = ws["X"][i].rows_view(g * ws["Bp"], ws["B"])
-                self.inputs.get((ws["B"], g, i), x, dst)
+                self.inputs.get((self._ws_key(ws["B"]), g, i), x, dst)
 
     # -- forward of the trunk for all groups --
     def trunk_forward(self, ws, train: bool, masks):
@@ -768,7 +785,7 @@ class TrunkEngine(EngineBase):
                            gamma=a.p(f"encoders.{i}.batchnorm.weight"), beta=a.p(f"encoders.{i}.batchnorm.bias"),
                            momentum=MOMENTUM, eps=EPS, train=int(train), act=1, p_drop=0.1 if train else 0.0,
                            mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
-                           seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=a.step.data_ptr(),
+                           seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=self.noise_step.data_ptr(),
                            out_hi=D.hi_ptr, out_lo=D.lo_ptr, ldp=D.ld, saved=ws["saved"][i][g].data_ptr(),
                            **_bn_ptrs(enc.batchnorm))
               E_p = ws["Ecat_p"].cols_view(i * self.Lp, self.latent)
@@ -802,13 +819,13 @@ class TrunkEngine(EngineBase):
                   # dWf[:, iL:(i+1)L] = dF^T * E_i        (beside it: needs dF only)
                   self._aux_run(i, lambda i=i, E_p=E_p: L.gemm(
                       Lt, Lt, R, ws["dF_p"], 1, E_p, 1, C_ptr=fptr(a.grad, a.offset["fusion_block.weight"] + i * Lt),
-                      ldc=self.n * Lt, splitk=-1, prezeroed=pz), after=ev)
+                      ldc=self.n * Lt, splitk=-1, prezeroed=pz, max_groups=self.aux_groups), after=ev)
               # dD_i = dE_i * W2_i (critical path) ; dW2_i = dE_i^T * D_i (beside it)
               ev = self._mark()
               L.gemm(R, h, Lt, dE, 0, self.wp(self.w2[i]), 1, C_ptr=ws["dD"][i].data_ptr(), ldc=hp)
               self._aux_run(i, lambda i=i, dE=dE, h=h: L.gemm(
                   Lt, h, R, dE, 1, ws["D"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_out.weight"), ldc=h, splitk=-1,
-                  prezeroed=pz), after=ev)
+                  prezeroed=pz, max_groups=self.aux_groups), after=ev)
               for g in range(G):
                   r0 = g * Bp
                   mask = None if masks is None else masks.get(f"{tags[g]}encoders.{i}.dropout")
@@ -819,7 +836,7 @@ class TrunkEngine(EngineBase):
                                    beta=a.p(f"encoders.{i}.batchnorm.bias"), saved=ws["saved"][i][g].data_ptr(), act=1,
                                    p_drop=0.1, mask=None if mask is None else mask.data_ptr(),
                                    ldm=0 if mask is None else mask.stride(0),
-                                   seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=a.step.data_ptr(),
+                                   seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=self.noise_step.data_ptr(),
                                    pre_act=0, sums=ws["sums"][i][g],
                                    dgamma=a.view(f"encoders.{i}.batchnorm.weight", a.grad),
                                    dbeta=a.view(f"encoders.{i}.batchnorm.bias", a.grad),
@@ -846,6 +863,7 @@ class TrunkEngine(EngineBase):
         hw = ws["heads"]
         y = self._labels(y)
         self.ensure_fresh()
+        self.noise_step.add_(1)                 # fresh dropout masks for this pass (forward and backward agree on them)
         self.stage_inputs(ws, x_groups)
         hw["acc"].zero_()
         # every gradient accumulator (stream-K wgrads, column-sum bias gradients, BatchNorm reduction scratch) is zeroed
@@ -891,6 +909,8 @@ class TrunkEngine(EngineBase):
         ws = self.workspace(B)
         hw = ws["heads"]
         self.ensure_fresh()
+        if train_mode:
+            self.noise_step.add_(1)
         self.stage_inputs(ws, x_groups)
         hw["acc"].zero_()
         self.trunk_forward(ws, train_mode, masks)
@@ -1009,8 +1029,9 @@ class VAEEngine(EngineBase):
         return full if i is None else full.cols_view(i * self.Lp, self.latent)
 
     def workspace(self, B: int) -> dict:
-        if B in self.ws:
-            return self.ws[B]
+        key = self._ws_key(B)
+        if key in self.ws:
+            return self.ws[key]
         dev, n, nd, Lt, Lp, P = self.device, self.ne, self.nd, self.latent, self.Lp, self.PRIOR
         mt = L.stat_tiles(B)
         f = lambda *shape: torch.zeros(*shape, device=dev)
@@ -1048,14 +1069,14 @@ class VAEEngine(EngineBase):
         ws["cs_zz"], ws["cs_tz"], ws["cs_tt"] = f(B), f(nd, B), f(nd, P)
         ws["KT"] = f(nd, B, Lp)
         ws["heads"] = self.heads.workspace(B)
-        self.ws[B] = ws
+        self.ws[key] = ws
         return ws
 
     def stage_inputs(self, ws, x_list: Sequence[torch.Tensor], targets: Optional[Sequence[torch.Tensor]] = None):
         """x_list: one matrix per encoder; targets: one per decoder (default: the inputs themselves, supervised_vae)."""
         for i, x in enumerate(x_list):
             x = self._input(x)
-            self.inputs.get((ws["B"], i), x, ws["X"][i])
+            self.inputs.get((self._ws_key(ws["B"]), i), x, ws["X"][i])
             if targets is None:
                 ws["x_f32"][i] = x                  # the reconstruction error reads the fp32 input
         if targets is not None:
@@ -1117,7 +1138,7 @@ class VAEEngine(EngineBase):
         if "epsilon" in noise:
             ws["eps"][:, :Lt].copy_(noise["epsilon"])
         else:
-            L.randn(ws["eps"].data_ptr(), Lp, B, Lt, self.seed + 11, a.step.data_ptr())
+            L.randn(ws["eps"].data_ptr(), Lp, B, Lt, self.seed + 11, self.noise_step.data_ptr())
         L.reparam_fwd(ws["mean"].data_ptr(), ws["s"].data_ptr(), ws["eps"].data_ptr(), Lp, B, Lt, ws["z"].data_ptr(),
                       ws["z_p"])
         # decoders, and beside them (aux stream) the heads and the MMD chain. The aux chain is queued FIRST: the Decoder
@@ -1162,7 +1183,7 @@ class VAEEngine(EngineBase):
             if f"mmd_prior.{i}" in noise:
                 T[:, :Lt].copy_(noise[f"mmd_prior.{i}"])
             else:
-                L.randn(T.data_ptr(), Lp, P, Lt, self.seed + 101 + i, a.step.data_ptr())
+                L.randn(T.data_ptr(), Lp, P, Lt, self.seed + 101 + i, self.noise_step.data_ptr())
             L.split_planes(T[:, :Lt], ws["T_p"][i])
             L.row_sqnorm(T.data_ptr(), Lp, P, Lt, ws["rt"][i].data_ptr())
             L.gemm(P, B, Lt, ws["T_p"][i], 0, ws["z_p"], 0, out=ws["Ktz_p"][i], epi_act=7,
@@ -1181,6 +1202,7 @@ class VAEEngine(EngineBase):
         n, nd, Lt, Lp, P = self.ne, self.nd, self.latent, self.Lp, self.PRIOR
         y = self._labels(y)
         self.ensure_fresh()
+        self.noise_step.add_(1)                 # fresh epsilon / MMD prior / dropout for this pass
         self.stage_inputs(ws, x_list, targets)
         self._forward(ws, y, True, masks, True, backward=True)
         w_mmd = fptr(ws["wts"], self.mmd_slot)
@@ -1242,6 +1264,7 @@ class VAEEngine(EngineBase):
         targets = x_groups[1] if len(x_groups) > 1 else None
         ws = self.workspace(x_list[0].shape[0])
         self.ensure_fresh()
+        self.noise_step.add_(1)                 # the reference draws a new epsilon in every forward, eval mode included
         self.stage_inputs(ws, x_list, targets)
         yl = self._labels(y) if y is not None else None
         self._forward(ws, yl, train_mode, masks, y is not None, want_xhat)
@@ -1257,17 +1280,18 @@ class VAEEngine(EngineBase):
 def build_gcn_csr(edge_index: torch.Tensor, num_nodes: int, device, conv: str = "GCN"):
     """The graph of a flexGCN layer as two CSRs: by destination (forward / weight gradient) and by source (input
     gradient), built once per model; edges of one row keep their edge_index order so sums are reproducible.
-      GCN : gcn_norm of torch_geometric (add the missing self loops, in-degree on the directed list as given,
-            w = deg_src^-1/2 * deg_dst^-1/2);
+      GCN : gcn_norm of torch_geometric (add_remaining_self_loops: one unit self loop per node whatever the input holds,
+            in-degree on the directed list as given, w = deg_src^-1/2 * deg_dst^-1/2);
       GC  : GraphConv's sum over the directed list as given, w = 1;
       SAGE: SAGEConv's mean, w = 1 / in-degree of the destination."""
     ei = edge_index.to("cpu", torch.long)
     src, dst = ei[0], ei[1]
     if conv == "GCN":
-        looped = torch.zeros(num_nodes, dtype=torch.bool)
-        looped[src[src == dst]] = True
-        extra = torch.nonzero(~looped).flatten()
-        src, dst = torch.cat([src, extra]), torch.cat([dst, extra])
+        # add_remaining_self_loops: self loops of the input are dropped and exactly one unit loop per node is appended
+        # (duplicated self loops collapse to one; duplicated ordinary edges stay)
+        keep = src != dst
+        loops = torch.arange(num_nodes)
+        src, dst = torch.cat([src[keep], loops]), torch.cat([dst[keep], loops])
         deg = torch.zeros(num_nodes, dtype=torch.float32).scatter_add_(0, dst, torch.ones(dst.numel()))
         dinv = deg.pow(-0.5)
         dinv[torch.isinf(dinv)] = 0
@@ -1319,8 +1343,9 @@ class GNNEngine(EngineBase):
         self._finish_init(0)
 
     def workspace(self, B: int) -> dict:
-        if B in self.ws:
-            return self.ws[B]
+        key = self._ws_key(B)
+        if key in self.ws:
+            return self.ws[key]
         dev, K, N, emb, Lt, Lp = self.device, self.K, self.N, self.emb, self.latent, self.Lp
         f = lambda *shape: torch.zeros(*shape, device=dev)
         ws = dict(B=B)
@@ -1340,7 +1365,7 @@ class GNNEngine(EngineBase):
         ws["dO"] = f(B * N, emb)
         ws["x"] = None
         ws["heads"] = self.heads.workspace(B)
-        self.ws[B] = ws
+        self.ws[key] = ws
         return ws
 
     def _conv_inputs(self, ws):
@@ -1374,7 +1399,7 @@ class GNNEngine(EngineBase):
                      tile_rows=rows, gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
                      momentum=MOMENTUM, eps=EPS, train=int(train), act=self.act, p_drop=self.p_drop if train else 0.0,
                      mask=None if mask is None else mask.data_ptr(), ldm=emb, seed=self.seed + 7 + 131 * k,
-                     seed_dev=a.step.data_ptr(), saved=ws["saved"][k].data_ptr(), **_bn_ptrs(enc.bns[k]), **kw)
+                     seed_dev=self.noise_step.data_ptr(), saved=ws["saved"][k].data_ptr(), **_bn_ptrs(enc.bns[k]), **kw)
         if not self.direct_planes:
             L.split_planes(ws["Dlast"].view(B, N * emb), ws["Dlast_p"])
         L.gemm(B, Lt, N * emb, ws["Dlast_p"], 0, self.wp(self.wfc), 0, C_ptr=ws["E"].data_ptr(), ldc=Lp,
@@ -1399,6 +1424,7 @@ class GNNEngine(EngineBase):
         rows = B * N
         y = self._labels(y)
         self.ensure_fresh()
+        self.noise_step.add_(1)
         self._stage(ws, x)
         self._forward(ws, y, True, masks, True, backward=True)
         # ---- backward ----
@@ -1413,7 +1439,7 @@ class GNNEngine(EngineBase):
                              gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
                              saved=ws["saved"][k].data_ptr(), act=self.act, p_drop=self.p_drop,
                              mask=None if mask is None else mask.data_ptr(), ldm=emb, seed=self.seed + 7 + 131 * k,
-                             seed_dev=a.step.data_ptr(), pre_act=0, sums=ws["sums"][k],
+                             seed_dev=self.noise_step.data_ptr(), pre_act=0, sums=ws["sums"][k],
                              dgamma=a.view(f"encoders.0.bns.{k}.weight", a.grad),
                              dbeta=a.view(f"encoders.0.bns.{k}.bias", a.grad), dV=ws["dO"].data_ptr(), ldd=emb)
             pw, pb, pr = (f"encoders.0.convs.{k}.{n}" if n else None for n in self.pn)
@@ -1429,6 +1455,8 @@ class GNNEngine(EngineBase):
         x = x_groups[0][0]
         ws = self.workspace(x.shape[0])
         self.ensure_fresh()
+        if train_mode:
+            self.noise_step.add_(1)
         self._stage(ws, x)
         yl = self._labels(y) if y is not None else None
         self._forward(ws, yl, train_mode, masks, y is not None)

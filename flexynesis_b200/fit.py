@@ -32,6 +32,18 @@ class GraphedStep:
                                       "kernels and runs eagerly: use model.fit_step, not a captured graph")
         lr = float(model.config["lr"] if lr is None else lr)
         eng.inputs.enabled = not resplit_inputs
+        eng.ws_tag = f"graph{id(self)}"            # private workspace: eager calls of the same batch size cannot alias it
+        try:
+            self._capture(model, batch, eng, lr, allreduce, grad_scale, warmup)
+        finally:
+            eng.ws_tag = ""
+
+    def _capture(self, model, batch, eng, lr, allreduce, grad_scale, warmup):
+        # The warm-up steps (they allocate the workspace and load every kernel before capture) must not count as training:
+        # parameters, Adam moments, counters and BatchNorm buffers are put back afterwards, so the first replay is step 1.
+        a = eng.arena
+        saved = [t.clone() for t in (a.flat, a.exp_avg, a.exp_avg_sq, a.step, eng.noise_step)]
+        bufs = [(b, b.clone()) for b in model.buffers()]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -42,6 +54,12 @@ class GraphedStep:
                     allreduce.step(lr)
                 else:
                     self.ws = model.fit_step(batch, lr=lr, allreduce=allreduce, grad_scale=grad_scale)
+            with torch.no_grad():
+                for dst, src in zip((a.flat, a.exp_avg, a.exp_avg_sq, a.step, eng.noise_step), saved):
+                    dst.copy_(src)
+                for b, src in bufs:
+                    b.copy_(src)
+            eng.wplanes.refresh()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         n0 = L.launch_count()
@@ -51,15 +69,19 @@ class GraphedStep:
                 self.ws = model.fit_step(batch, lr=lr, grad_scale=grad_scale)
         else:
             self.g1, self.g2 = torch.cuda.CUDAGraph(), None
+            self.fused_dp = hasattr(allreduce, "step") and getattr(allreduce, "capturable", False)
             with torch.cuda.graph(self.g1):
                 g, y = model._split_batch(batch)
                 self.ws = eng.forward_backward(g, y, None)
+                if self.fused_dp:                          # reduce-scatter / Adam / all-gather + in-stream barriers: same graph
+                    allreduce.step(lr)
             if not hasattr(allreduce, "step"):             # NCCL all-reduce + the single-GPU optimizer kernel
                 self.g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.g2):
                     eng.optimizer_step(lr, 1.0, grad_scale)
         self.lr = lr
-        self.launches_per_step = L.launch_count() - n0 + (3 if self.g2 is None and allreduce is not None else 0)
+        self.launches_per_step = L.launch_count() - n0 + (
+            3 if self.g2 is None and allreduce is not None and not getattr(self, "fused_dp", False) else 0)
 
     def __call__(self):
         self.g1.replay()
@@ -67,8 +89,8 @@ class GraphedStep:
             if self.g2 is not None:
                 self.allreduce(self.eng.arena.grad)
                 self.g2.replay()
-            else:
-                self.allreduce.step(self.lr)               # NvlsDataParallel: fused reduce-scatter / Adam / all-gather
+            elif not self.fused_dp:
+                self.allreduce.step(self.lr)               # NvlsDataParallel with host barriers: outside the graph
         return self.ws
 
     def losses(self) -> Dict[str, torch.Tensor]:
@@ -127,47 +149,68 @@ class HostStreamTrainer:
         return float(self.steps[k].losses()["__total__"])          # synchronises with the step, not with the copy
 
 
+def _validation_loss(model, val) -> float:
+    """Mean of validation_step over the batches of `val`, weighted by batch size (what Lightning's on_epoch mean logs)."""
+    tot, rows = 0.0, 0
+    for vb in val:
+        first = vb[0]
+        while isinstance(first, dict):
+            first = next(iter(first.values()))
+        n = int(first.shape[0])
+        tot += float(model.validation_step(vb, 0, log=False)) * n
+        rows += n
+    return tot / max(rows, 1)
+
+
 def fit(model, dataset, batch_size: int, epochs: int, device="cuda", val_dataset=None, seed: int = 0,
-        log_every: int = 0):
-    """Train `model` on `dataset` (MultiOmicDataset duck type) with the engine's fused steps. Returns the per-epoch
-    history [{'train_loss': ..., 'val_loss': ...}]."""
-    from .data import DeviceBatcher, DeviceTripletBatcher
+        log_every: int = 0, graph: bool = True):
+    """Train `model` on `dataset` with the engine's fused steps: the reference's Lightning policy (flexynesis/main.py:212-225,
+    :289-318: shuffled drop_last batches -> training_step -> backward -> clip_grad_norm_(1.0) -> Adam.step, a validation
+    pass per epoch) with the batch gathered ON THE DEVICE into static buffers and the whole step replayed from ONE CUDA
+    graph -- for mini-batches too (the reference's default regime, B in {32, 64, 128}, main.py:183-190): the batcher
+    refills the buffers, the captured step re-splits them into operand planes. `dataset` is a MultiOmicDataset duck type,
+    a TripletMultiOmicDataset (MultiTripletNetwork) or a MultiOmicDatasetNW (GNN: `node_features_tensor`). Validation runs
+    in batches of `batch_size` rows. Returns the per-epoch history [{'train_loss': ..., 'val_loss': ...}]."""
+    from .data import DeviceBatcher, DeviceNodeBatcher, DeviceTripletBatcher
     model.to(device)
     model.train()
-    if getattr(model, "main_var", None) is not None:       # MultiTripletNetwork: on-device triplet sampling
+    triplet = getattr(model, "main_var", None) is not None
+    graph_ds = hasattr(dataset, "node_features_tensor") and not hasattr(dataset, "dat")
+    if triplet:                                              # MultiTripletNetwork: on-device triplet sampling
         loader = DeviceTripletBatcher(dataset, model.main_var, batch_size, device, shuffle=True, drop_last=True, seed=seed)
         loader.full_batch = False
+    elif graph_ds:
+        loader = DeviceNodeBatcher(dataset, batch_size, device, shuffle=True, drop_last=True, seed=seed)
     else:
         loader = DeviceBatcher(dataset, batch_size, device, shuffle=True, drop_last=True, seed=seed)
     if val_dataset is None:
         val = None
-    elif getattr(model, "main_var", None) is not None:     # triplet batches for the validation objective as well
+    elif triplet:                                            # triplet batches for the validation objective as well
         vbase = getattr(val_dataset, "dataset", val_dataset)
         nval = int((~torch.isnan(torch.as_tensor(vbase.ann[model.main_var]).float())).sum())
-        val = DeviceTripletBatcher(val_dataset, model.main_var, max(nval, 1), device, shuffle=False, drop_last=False,
-                                   seed=seed + 1)
+        val = DeviceTripletBatcher(val_dataset, model.main_var, max(min(nval, batch_size), 1), device, shuffle=False,
+                                   drop_last=False, seed=seed + 1)
+    elif graph_ds:
+        val = DeviceNodeBatcher(val_dataset, min(len(val_dataset), batch_size), device, shuffle=False, drop_last=False)
     else:
-        val = DeviceBatcher(val_dataset, len(val_dataset), device, shuffle=False, drop_last=False)
+        val = DeviceBatcher(val_dataset, min(len(val_dataset), batch_size), device, shuffle=False, drop_last=False)
     history = []
     graphed = None
     for epoch in range(epochs):
         tot, nb = None, 0
         for batch in loader:
-            if loader.full_batch:
-                if graphed is None:
-                    graphed = GraphedStep(model, batch)
-                ws = graphed()
-            else:
-                ws = model.fit_step(batch)
+            if graph and graphed is None:
+                # full batch: the resident planes are split once; mini-batches: the split of the static buffers is captured
+                graphed = GraphedStep(model, batch, resplit_inputs=not loader.full_batch)
+            ws = graphed() if graph else model.fit_step(batch)
             t = model.engine().losses(ws)["__total__"].detach().clone()
             tot = t if tot is None else tot + t
             nb += 1
-        rec = {"train_loss": float(tot / max(nb, 1))}
+        rec = {"train_loss": float(tot / max(nb, 1)) if tot is not None else float("nan")}
         if val is not None:
             model.eval()
             with torch.no_grad():
-                for vb in val:
-                    rec["val_loss"] = float(model.validation_step(vb, 0, log=False))
+                rec["val_loss"] = _validation_loss(model, val)
             model.train()
         history.append(rec)
         if log_every and (epoch + 1) % log_every == 0:

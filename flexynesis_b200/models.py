@@ -160,11 +160,13 @@ class _EngineModel(_Base):
             self.log_dict(losses, on_step=False, on_epoch=True, prog_bar=True)
         return total
 
-    def validation_step(self, val_batch, batch_idx, log=True):
+    def validation_step(self, val_batch, batch_idx, log=True, masks=None):
+        """The reference's validation objective: the UNWEIGHTED sum of the loss terms (direct_pred.py:262-294). `masks`
+        (tests only): replayed Gaussian draws for the VAE families, whose forward samples in eval mode as well."""
         groups, y = self._split_batch(val_batch)
         dev = groups[0][0].device if groups[0][0].is_cuda else next(self.parameters()).device
         eng = self.engine(dev)
-        ws = eng.evaluate(groups, y, train_mode=self.training)
+        ws = eng.evaluate(groups, y, train_mode=self.training, masks=masks)
         vals = eng.losses(ws)
         total = vals["__val_total__"].detach().clone()      # unweighted sum (direct_pred.py:290)
         losses = {k: v.detach().clone() for k, v in vals.items() if not k.startswith("__")}

@@ -137,23 +137,41 @@ class NvlsDataParallel:
         self.begin = self.rank * per
         self.end = a.numel if self.rank == self.world - 1 else (self.rank + 1) * per
         self.scratch = torch.zeros(4, dtype=torch.float32, device=a.device)        # 16 bytes: double sum + counter
+        # in-stream barrier state (csrc/dp.cu dp_barrier_kernel): symmetric arrival counters + a local epoch counter
+        self.flags = symm_mem.empty(16, dtype=torch.int32, device=a.device)
+        self.flags.zero_()
+        self.h_flags = symm_mem.rendezvous(self.flags, group)
+        self.epoch = torch.zeros(16, dtype=torch.int32, device=a.device)
+        self.host_barriers = bool(int(__import__("os").environ.get("FXN_DP_HOST_BARRIERS", "0"))) or not self.h_flags.multicast_ptr
         # make every rank start from rank 0's parameters
         dist.broadcast(a.flat, 0, group=group)
         eng.wplanes.refresh()
         torch.cuda.synchronize()
         self.h_flat.barrier(channel=0)
 
+    def _barrier(self, handle):
+        if self.host_barriers:                           # torch symmetric-memory barrier, enqueued by the host (not capturable)
+            handle.barrier(channel=0)
+        else:                                            # one device thread per rank, in stream order (capturable)
+            self.L.dp_barrier(self.h_flags.multicast_ptr, self.flags.data_ptr(), self.epoch.data_ptr(), 0, self.world)
+
+    @property
+    def capturable(self) -> bool:
+        return not self.host_barriers
+
     def step(self, lr: float, max_norm: float = 1.0):
-        """Collective: call on every rank after its backward pass has been queued on the current stream."""
+        """Collective: call on every rank after its backward pass has been queued on the current stream. With the
+        in-stream barriers the whole sequence is plain kernel launches and can be captured in the same CUDA graph as the
+        backward pass."""
         L, a = self.L, self.eng.arena
-        self.h_grad.barrier(channel=0)                   # every rank's gradients are complete and visible
+        self._barrier(self.h_grad)                       # every rank's gradients are complete and visible
         L.dp_reduce_sumsq(self.h_grad.multicast_ptr, a.grad.data_ptr(), self.begin, self.end, 1.0 / self.world,
                           self.h_part.multicast_ptr, self.rank, self.scratch.data_ptr(), a.step.data_ptr())
-        self.h_part.barrier(channel=0)                   # all partial norms have landed everywhere
+        self._barrier(self.h_part)                       # all partial norms have landed everywhere
         L.dp_adam_bcast(self.h_flat.multicast_ptr, a.flat.data_ptr(), a.grad.data_ptr(), a.exp_avg.data_ptr(),
                         a.exp_avg_sq.data_ptr(), self.begin, self.end, self.partials.data_ptr(), self.world, lr, max_norm,
                         a.step.data_ptr(), a.grad_norm.data_ptr())
-        self.h_flat.barrier(channel=0)                   # all slices of the new parameters have landed
+        self._barrier(self.h_flat)                       # all slices of the new parameters have landed
         self.eng.wplanes.refresh()
 
 

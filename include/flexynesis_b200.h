@@ -320,6 +320,11 @@ int fxn_dp_reduce_sumsq(const void* mc_grad, float* grad_local, long long begin,
 int fxn_dp_adam_bcast(void* mc_param, const float* param_local, const float* grad_local, float* exp_avg, float* exp_avg_sq,
                       long long begin, long long end, const float* partials, int world, float lr, float beta1, float beta2,
                       float eps, float max_norm, const long long* step_counter, float* norm_out, void* stream);
+/* Barrier between the ranks of a data-parallel job, executed in stream order by one device thread per rank: mc_flags is
+ * the multicast address of a symmetric uint32[16] array (zeroed once), local_flags this rank's copy, epoch a local device
+ * uint32[16] (zeroed once). Every rank must issue the same sequence of barriers. Capturable in a CUDA graph. */
+int fxn_dp_barrier(void* mc_flags, const void* local_flags, void* epoch, int slot, int world, void* stream);
+
 /* Refresh the operand planes of many weight matrices in one launch. segments_dev: device array of nseg records
  * {int64 src_off, rows, cols, ld_src, dst_off, ldp} (element offsets into src / the plane arenas). */
 int fxn_split_planes_multi(const float* src, const void* segments_dev, int nseg, long long max_seg_elems, void* hi,

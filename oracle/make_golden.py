@@ -116,6 +116,23 @@ def eval_forward(model, spec, batch):
     return {k: v.clone() for k, v in ev.items()}
 
 
+def validation_record(model, spec, batch):
+    """The reference's validation_step on the batch in eval mode (direct_pred.py:262-294 and the other families' own
+    versions): returned loss (= the UNWEIGHTED sum of the loss terms, :290), the logged per-variable losses, and the
+    Gaussian draws it made (supervised_vae / CrossModalPred sample epsilon and the MMD prior in eval mode too)."""
+    model.eval()
+    logged = {}
+    orig_log = getattr(model, "log_dict", None)
+    model.log_dict = lambda d, **k: logged.update({kk: vv.detach().clone() for kk, vv in d.items()})
+    with ref_shim.NoiseRecorder(model, triplet=(spec.model == "MultiTripletNetwork")) as rec:
+        torch.manual_seed(77)
+        with torch.no_grad():
+            loss = model.validation_step(batch, 0)
+    if orig_log is not None:
+        model.log_dict = orig_log
+    return dict(total=loss.detach().clone(), losses=logged, noise={k: v.detach().clone() for k, v in rec.record.items()})
+
+
 def run_reference(name: str, sc) -> dict:
     ref = ref_shim.load()
     spec: Spec = sc["spec"]
@@ -125,6 +142,7 @@ def run_reference(name: str, sc) -> dict:
                             edge_index)
     P0 = copy.deepcopy(model.state_dict())
     ev0 = eval_forward(model, spec, batch)
+    val0 = validation_record(model, spec, batch)
     model.train()
     opt = model.configure_optimizers()
     steps = []
@@ -164,7 +182,7 @@ def run_reference(name: str, sc) -> dict:
     ev = eval_forward(model, spec, batch)
     return dict(name=name, spec=spec.__dict__, lr=LR, batch=batch, edge_index=edge_index, P0=P0, steps=steps,
                 P_final=copy.deepcopy(model.state_dict()),
-                eval_outputs0=ev0, eval_outputs=ev)
+                eval_outputs0=ev0, eval_outputs=ev, val0=val0)
 
 
 def significant_elements(step_grads, thresh=1e-3, global_thresh=1e-5):
@@ -204,6 +222,12 @@ def check_oracle(g: dict, rtol=2e-5, atol=2e-6) -> float:
         res = forward(P, spec, g["batch"], False, Noise({}), g["edge_index"])
         for k, v in g["eval_outputs0"].items():
             cmp(f"initial eval outputs[{k}]", res["outputs"][k], v)
+    if g.get("val0") is not None:
+        res = forward(P, spec, g["batch"], False, Noise(g["val0"]["noise"]), g["edge_index"])
+        cmp("validation_step total (unweighted sum)", res["val_total"], g["val0"]["total"])
+        for k, v in g["val0"]["losses"].items():
+            if k != "val_loss":
+                cmp(f"validation_step loss[{k}]", res["losses"][k], v)
     tr = Trainer(P, spec, g["lr"], edge_index=g["edge_index"])
     for s, st in enumerate(g["steps"]):
         res = tr.step(g["batch"], Noise(st["noise"]))

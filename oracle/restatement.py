@@ -185,17 +185,17 @@ def triplet(anchor: Tensor, positive: Tensor, negative: Tensor, margin: float = 
 # GCNConv (torch_geometric, restated; A6 of SURVEY.md)
 # ----------------------------------------------------------------------------------------------------
 def gcn_norm(edge_index: Tensor, num_nodes: int, dtype=torch.float32) -> Tuple[Tensor, Tensor, Tensor]:
-    """PyG gcn_norm(add_self_loops=True, improved=False, flow='source_to_target'): add the *remaining* self
-    loops with weight 1, deg = in-degree over targets (edge_index[1]) on the directed list as given,
-    w_e = deg^-1/2[src] * deg^-1/2[dst], inf -> 0."""
+    """PyG gcn_norm(add_self_loops=True, improved=False, flow='source_to_target') with edge_weight=None: the edge list
+    goes through add_remaining_self_loops(fill_value=1) -- every self loop present in the input is REMOVED and exactly one
+    self loop per node (weight 1: the unit weight of an existing loop, or the fill value) is appended, so duplicated
+    self loops collapse to one while duplicated ordinary edges stay (torch_geometric/utils/loop.py); then
+    deg = in-degree over targets (edge_index[1]) on the directed list, w_e = deg^-1/2[src] * deg^-1/2[dst], inf -> 0."""
     src, dst = edge_index[0].long(), edge_index[1].long()
+    keep = src != dst
+    loops = torch.arange(num_nodes)
+    src = torch.cat([src[keep], loops])
+    dst = torch.cat([dst[keep], loops])
     w = torch.ones(src.numel(), dtype=dtype)
-    has_loop = torch.zeros(num_nodes, dtype=torch.bool)
-    has_loop[src[src == dst]] = True
-    missing = torch.nonzero(~has_loop).flatten()
-    src = torch.cat([src, missing])
-    dst = torch.cat([dst, missing])
-    w = torch.cat([w, torch.ones(missing.numel(), dtype=dtype)])
     deg = torch.zeros(num_nodes, dtype=dtype).scatter_add_(0, dst, w)
     dinv = deg.pow(-0.5)
     dinv[torch.isinf(dinv)] = 0

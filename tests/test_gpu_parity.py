@@ -120,8 +120,12 @@ class Report:
         err = float((got - ref).abs().max())
         if not err <= atol + rtol * scale:
             self.errors.append(f"{tag}: abs err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e})")
+        if keep is not None:
+            self.skipped = getattr(self, "skipped", 0) + int((~keep).sum())
 
     def finish(self):
+        if getattr(self, "skipped", 0):
+            print(f"[parity] {self.skipped} gradient elements excluded (hidden units with a ReLU gate within 2e-4 of zero)")
         assert not self.errors, "\n".join(self.errors)
 
 

@@ -1,0 +1,331 @@
+"""GPU tests added in round 2: the production random-number path (in-kernel Philox dropout, Gaussian draws), the noise
+counter, validation_step against the reference's recorded values, MultiTripletNetwork at ragged and full size, the GPU
+inference wrappers (predict / transform / deepcopy / torch.save), graphed mini-batch fit() incl. the GNN dataset, and the
+workspace isolation of captured graphs."""
+import copy
+import glob
+import io
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.restatement import Noise, Spec, forward, synthetic_batch, synthetic_graph
+from test_gpu_parity import (CASES, GOLDEN_DIR, Report, _DS, _GDS, build_model, compare_step, masks_from_noise,
+                             oracle_reference, sync_state, to_cuda)
+
+pytestmark = pytest.mark.gpu
+VT = {"y": "numerical", "c": "categorical", "e": "numerical", "t": "numerical"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# production RNG
+# ----------------------------------------------------------------------------------------------------------------
+def _bn_problem(rows, cols, seed):
+    from flexynesis_b200 import _lib as L
+    g = torch.Generator().manual_seed(seed)
+    ld = L.pad8(cols)
+    V = torch.zeros(rows, ld)
+    V[:, :cols] = torch.randn(rows, cols, generator=g)
+    V = V.cuda()
+    nt = L.stat_tiles(rows)
+    partials = torch.zeros(nt * 2 * cols, device="cuda")
+    L.col_stats(V.data_ptr(), ld, rows, cols, 128, partials.data_ptr())
+    return dict(V=V, ld=ld, nt=nt, partials=partials, gamma=torch.ones(cols, device="cuda"),
+                beta=torch.full((cols,), 8.0, device="cuda"),           # BN output > 0 everywhere: ReLU never gates
+                rm=torch.zeros(cols, device="cuda"), rv=torch.ones(cols, device="cuda"),
+                nbt=torch.zeros(1, dtype=torch.int64, device="cuda"), saved=torch.zeros(2 * cols, device="cuda"))
+
+
+def _dropout_forward(pr, rows, cols, p, seed, counter):
+    from flexynesis_b200 import _lib as L
+    out = torch.zeros(rows, cols, device="cuda")
+    L.bn_fwd(V=pr["V"].data_ptr(), ldv=pr["ld"], rows=rows, cols=cols, partials=pr["partials"].data_ptr(), ntiles=pr["nt"],
+             tile_rows=128, gamma=pr["gamma"].data_ptr(), beta=pr["beta"].data_ptr(), running_mean=pr["rm"].data_ptr(),
+             running_var=pr["rv"].data_ptr(), num_batches_tracked=pr["nbt"].data_ptr(), momentum=0.1, eps=1e-5, train=1,
+             act=1, p_drop=p, seed=seed, seed_dev=counter.data_ptr(), out=out.data_ptr(), ldo=cols,
+             saved=pr["saved"].data_ptr())
+    return out != 0
+
+
+@pytest.mark.parametrize("p", [0.1, 0.2])
+def test_philox_dropout_forward_and_backward_draw_the_same_mask(p):
+    """The mask is never stored: the backward kernels regenerate it from (seed, counter, element). Forward mask from
+    fxn_bn_act_fwd (affine shift keeps every activation positive, so zeros are exactly the dropped elements); backward mask
+    decoded from the column reductions of fxn_bn_act_bwd (phase 1) with dOut = 2^(row % 12) on one 12-row group at a time.
+    Also: keep rate, a fresh mask when the device counter advances, the same mask when it does not."""
+    from flexynesis_b200 import _lib as L
+    rows, cols, seed = 777, 203, 0x1234
+    pr = _bn_problem(rows, cols, 5)
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    m0 = _dropout_forward(pr, rows, cols, p, seed, counter)
+    n = rows * cols
+    keep = float(m0.float().mean())
+    assert abs(keep - (1 - p)) < 5 * math.sqrt(p * (1 - p) / n), keep
+    scale = 1.0 / (1.0 - p)
+    ldg = pr["ld"]
+    for r0 in range(0, rows, 12):
+        r1 = min(rows, r0 + 12)
+        dOut = torch.zeros(rows, ldg, device="cuda")
+        dOut[r0:r1, :cols] = (2.0 ** torch.arange(r1 - r0, device="cuda"))[:, None]
+        sums = torch.zeros(2 * cols, device="cuda")
+        L.bn_bwd(V=pr["V"].data_ptr(), ldv=pr["ld"], dOut=dOut.data_ptr(), ldg=ldg, rows=rows, cols=cols,
+                 gamma=pr["gamma"].data_ptr(), beta=pr["beta"].data_ptr(), saved=pr["saved"].data_ptr(), act=1, p_drop=p,
+                 seed=seed, seed_dev=counter.data_ptr(), pre_act=0, sums=sums.data_ptr(), phase=1)
+        want = (m0[r0:r1].float() * (2.0 ** torch.arange(r1 - r0, device="cuda"))[:, None]).sum(0) * scale
+        assert torch.allclose(sums[:cols], want, rtol=1e-5, atol=0), f"rows {r0}..{r1}: backward mask differs"
+    counter.fill_(1)
+    m1 = _dropout_forward(pr, rows, cols, p, seed, counter)
+    assert float((m1 != m0).float().mean()) > p                      # independent draws disagree on ~2p(1-p) of the elements
+    counter.fill_(0)
+    assert torch.equal(_dropout_forward(pr, rows, cols, p, seed, counter), m0)
+    assert not torch.equal(_dropout_forward(pr, rows, cols, p, seed + 1, counter), m0)
+
+
+def test_randn_is_standard_normal_and_fresh_per_counter():
+    from scipy import stats
+    from flexynesis_b200 import _lib as L
+    rows, cols, ld = 512, 250, 256
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def draw(seed):
+        out = torch.zeros(rows, ld, device="cuda")
+        L.randn(out.data_ptr(), ld, rows, cols, seed, counter.data_ptr())
+        assert float(out[:, cols:].abs().max()) == 0.0              # padding untouched
+        return out[:, :cols].contiguous()
+    a = draw(11)
+    x = a.double().flatten().cpu().numpy()
+    n = x.size
+    assert abs(x.mean()) < 5 / math.sqrt(n)
+    assert abs(x.var() - 1) < 5 * math.sqrt(2 / n)
+    assert abs(stats.skew(x)) < 5 * math.sqrt(6 / n) and abs(stats.kurtosis(x)) < 5 * math.sqrt(24 / n)
+    assert stats.kstest(x, "norm").pvalue > 1e-4
+    assert torch.equal(draw(11), a)
+    counter.fill_(3)
+    b = draw(11)
+    assert not torch.equal(a, b)
+    assert abs(float(torch.corrcoef(torch.stack([a.flatten(), b.flatten()]))[0, 1])) < 5 / math.sqrt(n)
+    # neighbouring rows / columns are uncorrelated
+    assert abs(float(torch.corrcoef(torch.stack([a[:-1].flatten(), a[1:].flatten()]))[0, 1])) < 5 / math.sqrt(n)
+    assert abs(float(torch.corrcoef(torch.stack([a[:, :-1].flatten(), a[:, 1:].flatten()]))[0, 1])) < 5 / math.sqrt(n)
+
+
+def test_noise_advances_every_forward_even_without_the_engine_optimizer():
+    """ADVICE (round 1): under a Lightning-style loop (training_step -> backward -> torch optimizer) the engine's Adam
+    counter never moves; dropout masks, epsilon and the MMD prior must still be fresh in every step, and models created
+    under different torch seeds must not share a noise stream."""
+    spec = CASES["cfg2_small"][0]
+    dat, y = synthetic_batch(spec, 256, 0)
+    torch.manual_seed(1)
+    model = build_model(spec, (dat, y, None), 1e-3)
+    model.train()
+    cb = to_cuda((dat, y, None))
+    eng = model.engine()
+    model.training_step(cb, 0, log=False)
+    ws = eng.ws[256]
+    d0 = (ws["D"][0].hi != 0).clone()
+    model.training_step(cb, 0, log=False)                      # no optimizer step in between
+    d1 = ws["D"][0].hi != 0
+    assert float((d0 != d1).float().mean()) > 0.05
+    torch.manual_seed(2)
+    other = build_model(spec, (dat, y, None), 1e-3)
+    assert other.engine().seed != eng.seed
+    vspec = CASES["svae_heads"][0]
+    vdat, vy = synthetic_batch(vspec, 128, 0)
+    vae = build_model(vspec, (vdat, vy, None), 1e-3)
+    vae.train()
+    vb = to_cuda((vdat, vy, None))
+    veng = vae.engine()
+    vae.training_step(vb, 0, log=False)
+    e0, t0 = veng.ws[128]["eps"].clone(), veng.ws[128]["T"][0].clone()
+    vae.training_step(vb, 0, log=False)
+    assert not torch.equal(veng.ws[128]["eps"], e0) and not torch.equal(veng.ws[128]["T"][0], t0)
+    vae.eval()
+    with torch.no_grad():
+        z0 = vae.forward([x for x in vb[0].values()])[1].clone()
+        z1 = vae.forward([x for x in vb[0].values()])[1]
+    assert not torch.equal(z0, z1)                             # the reference samples epsilon in eval mode as well
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# validation_step against the reference's recorded values
+# ----------------------------------------------------------------------------------------------------------------
+GOLDEN = sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-3] for p in GOLDEN])
+def test_validation_step_matches_reference_golden(path):
+    """validation_step in eval mode at the reference's initial state (direct_pred.py:262-294 and the other families'
+    versions): the returned value is the UNWEIGHTED sum of the loss terms; per-variable losses as logged."""
+    g = torch.load(path, weights_only=False)
+    spec = Spec(**g["spec"])
+    model = build_model(spec, g["batch"], g["lr"], g["P0"], g.get("edge_index"))
+    model.eval()
+    cb = to_cuda(g["batch"])
+    with torch.no_grad():
+        total = model.validation_step(cb, 0, log=False, masks=masks_from_noise(g["val0"]["noise"]))
+    rep = Report()
+    rep.close("val_loss", total, g["val0"]["total"])
+    eng = model.engine()
+    B = next(iter(g["batch"][0].values())).shape[0] if isinstance(g["batch"][0], dict) else g["batch"][0].shape[0]
+    vals = eng.losses(eng.ws[B])
+    for k, v in g["val0"]["losses"].items():
+        if k != "val_loss":
+            rep.close(f"val loss[{k}]", vals[k], v, atol=1e-5)
+    rep.close("val_loss == unweighted sum", total, sum(v for k, v in g["val0"]["losses"].items() if k != "val_loss"))
+    rep.finish()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# MultiTripletNetwork beyond the toy golden
+# ----------------------------------------------------------------------------------------------------------------
+def _triplet_batch(spec, B, seed):
+    dat, y = synthetic_batch(spec, B, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    pos = {k: torch.randn(v.shape, generator=g) for k, v in dat.items()}
+    neg = {k: torch.randn(v.shape, generator=g) for k, v in dat.items()}
+    return (dat, pos, neg, y)
+
+
+TRIPLET = {
+    # ragged everywhere: B = 333 (each of the three row groups straddles 128-row tiles), odd hidden widths, two heads
+    "ragged": (Spec(model="MultiTripletNetwork", input_dims=[700, 300], latent_dim=48, hidden_dim_factor=0.2,
+                    supervisor_hidden_dim=16, variables=["c", "y"], variable_types=VT, num_classes={"c": 4}), 333, 3),
+    # BASELINE config 2's shapes: [4096 x 5000] + [4096 x 3000] per row group, three groups through every GEMM
+    "cfg2_size": (Spec(model="MultiTripletNetwork", input_dims=[5000, 3000], latent_dim=256, hidden_dim_factor=0.1024,
+                       supervisor_hidden_dim=32, variables=["c"], variable_types=VT, num_classes={"c": 5}), 4096, 1),
+}
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("name", list(TRIPLET))
+def test_triplet_matches_oracle(name):
+    spec, B, nsteps = TRIPLET[name]
+    batch = _triplet_batch(spec, B, 0)
+    P0, batch, steps, _ = oracle_reference(spec, B, 1e-3, steps=nsteps, batch=batch)
+    model = build_model(spec, batch, 1e-3, P0)
+    model.train()
+    cb = to_cuda(batch)
+    rep = Report()
+    for s, st in enumerate(steps):
+        sync_state(model, st["P_before"])
+        compare_step(rep, model, spec, batch, cb, st, s, st["P_before"], 1e-3)
+        skipped = {k: int(v.sum()) for k, v in st["flagged"].items() if bool(v.any())}
+        print(f"[{name}] step {s}: hidden units excluded for a ReLU gate within 2e-4 of zero: {skipped or 'none'}")
+    rep.finish()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU inference wrappers and object round trips
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("family", ["DirectPred", "supervised_vae", "MultiTripletNetwork"])
+def test_gpu_predict_transform_deepcopy_and_pickle(family):
+    """predict() / transform() on the GPU (4096-row batches through the engine) against the same model's CPU torch path;
+    deepcopy and torch.save/torch.load of a GPU-trained model give a working, equal model (main.py:580, __main__.py:1562)."""
+    import flexynesis_b200 as fx
+    vt = {"y": "numerical", "c": "categorical"}
+    n = 5000                                            # more than one 4096-row inference batch
+    ds = fx.SyntheticMultiOmicDataset([90, 40], n, vt, {"c": 3}, seed=0)
+    view = _DS(ds.dat, ds.ann, vt)
+    view.samples = ds.samples
+    cfg = {"latent_dim": 24, "hidden_dim_factor": 0.25, "supervisor_hidden_dim": 8, "lr": 1e-3}
+    torch.manual_seed(0)
+    model = getattr(fx, family)(cfg, view, ["c", "y"], device_type="gpu").cuda().train()
+    sub = {k: v[:512].cuda() for k, v in ds.dat.items()}
+    ysub = {k: v[:512].cuda() for k, v in ds.ann.items()}
+    batch = (sub, sub, sub, ysub) if family == "MultiTripletNetwork" else (sub, ysub, None)
+    for _ in range(3):
+        model.fit_step(batch)
+    torch.cuda.synchronize()
+    pred = model.predict(view)
+    emb = model.transform(view)
+    assert pred["c"].shape == (n, 3) and pred["y"].shape == (n, 1) and emb.shape == (n, 24)
+    assert list(emb.index) == list(ds.samples) and list(emb.columns) == [f"E{i}" for i in range(24)]
+    assert np.allclose(pred["c"].sum(1), 1.0, atol=1e-5)
+    clone = copy.deepcopy(model)
+    buf = io.BytesIO()
+    torch.save(model, buf)
+    buf.seek(0)
+    loaded = torch.load(buf, weights_only=False)
+    if family != "supervised_vae":                      # the VAE's embedding is sampled: compare its deterministic parts below
+        for other in (clone, loaded):
+            p2 = other.predict(view)
+            assert np.allclose(p2["c"], pred["c"], atol=1e-5) and np.allclose(p2["y"], pred["y"], atol=1e-5)
+        cpu = copy.deepcopy(model)
+        cpu.device_type = "cpu"
+        p3 = cpu.predict(view)                          # plain torch containers on the CPU
+        assert np.allclose(p3["c"], pred["c"], atol=2e-3) and np.allclose(p3["y"], pred["y"], rtol=2e-3, atol=2e-3)
+        e3 = cpu.transform(view)
+        assert np.allclose(e3.to_numpy(), emb.to_numpy(), rtol=2e-3, atol=2e-3)
+    for other in (clone, loaded):
+        sd, sd2 = model.state_dict(), other.state_dict()
+        assert sd.keys() == sd2.keys() and all(torch.equal(sd[k].cpu(), sd2[k].cpu()) for k in sd)
+        other.cuda().train()
+        other.fit_step(batch)                           # the copy trains on its own arena
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fit(): graphed mini-batches, GNN dataset, validation in batches, workspace isolation
+# ----------------------------------------------------------------------------------------------------------------
+def test_graphed_minibatch_step_equals_the_eager_step():
+    """fit() replays ONE captured step for every mini-batch (static batch buffers re-split inside the graph). With dropout
+    masks disabled (p = 0 through eval-free determinism is not available), compare through the loss trajectory of two runs
+    from the same seed: graph=True and graph=False must produce the same losses up to fp32 summation order."""
+    import flexynesis_b200 as fx
+    vt = {"y": "numerical", "c": "categorical"}
+    tr = fx.SyntheticMultiOmicDataset([120, 60], 512, vt, {"c": 3}, seed=0)
+    view = _DS(tr.dat, tr.ann, vt)
+    cfg = {"latent_dim": 16, "hidden_dim_factor": 0.25, "supervisor_hidden_dim": 8, "lr": 5e-3}
+    hist = []
+    for graph in (True, False):
+        torch.manual_seed(0)
+        m = fx.DirectPred(cfg, view, ["c", "y"], device_type="gpu")
+        hist.append(fx.fit.fit(m, tr, batch_size=128, epochs=3, seed=3, graph=graph))
+    for a, b in zip(*hist):
+        assert abs(a["train_loss"] - b["train_loss"]) <= 2e-3 * abs(b["train_loss"]), (a, b)
+
+
+def test_fit_trains_the_gnn_on_a_network_dataset_with_batched_validation():
+    import flexynesis_b200 as fx
+    spec = Spec(model="GNN", input_dims=[2], latent_dim=16, supervisor_hidden_dim=8, variables=["y"], variable_types=VT,
+                node_count=60, node_embedding_dim=8, num_convs=2, activation="relu")
+    ei = synthetic_graph(60, 200, 0)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(384, 60, 2, generator=g)
+    yv = x[:, :5, 0].sum(1)                                  # learnable target
+    ds = _GDS(x, {"y": yv}, {"y": "numerical"}, ei)
+    ds.ann = {"y": yv}
+    va = _GDS(x[:100], {"y": yv[:100]}, {"y": "numerical"}, ei)
+    va.ann = {"y": yv[:100]}
+    cfg = {"latent_dim": 16, "supervisor_hidden_dim": 8, "lr": 5e-3, "node_embedding_dim": 8, "num_convs": 2,
+           "activation": "relu", "hidden_dim_factor": 0.0}
+    torch.manual_seed(0)
+    m = fx.GNN(cfg, ds, ["y"], device_type="gpu", gnn_conv_type="GCN")
+    hist = fx.fit.fit(m, ds, batch_size=64, epochs=8, val_dataset=va)        # validation: 64 + 36 rows
+    assert all(np.isfinite(h["train_loss"]) and np.isfinite(h["val_loss"]) for h in hist)
+    assert min(h["train_loss"] for h in hist[-2:]) < hist[0]["train_loss"]
+
+
+def test_validation_of_equal_size_cannot_alias_the_captured_training_batch():
+    """ADVICE (round 1): a full-batch graph reads its input planes without re-splitting them; validating a set with the
+    SAME number of rows must not overwrite them. Training with and without the interleaved validation gives the same
+    parameters."""
+    import flexynesis_b200 as fx
+    vt = {"y": "numerical", "c": "categorical"}
+    tr = fx.SyntheticMultiOmicDataset([80, 40], 256, vt, {"c": 3}, seed=0)
+    va = fx.SyntheticMultiOmicDataset([80, 40], 256, vt, {"c": 3}, seed=9)
+    view = _DS(tr.dat, tr.ann, vt)
+    cfg = {"latent_dim": 16, "hidden_dim_factor": 0.25, "supervisor_hidden_dim": 8, "lr": 5e-3}
+    out = []
+    for val in (None, va):
+        torch.manual_seed(0)
+        m = fx.DirectPred(cfg, view, ["c", "y"], device_type="gpu")
+        fx.fit.fit(m, tr, batch_size=256, epochs=4, val_dataset=val, seed=1)
+        out.append({k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
+    # two runs differ by atomics-order noise that Adam's sign-like first steps amplify to ~1e-4; training three of the four
+    # steps on the validation features (the aliasing bug) moves the weights by O(lr) = 5e-3 per element
+    num = sum(float((out[0][k] - out[1][k]).double().pow(2).sum()) for k in out[0] if out[0][k].dtype.is_floating_point)
+    den = sum(float(out[0][k].double().pow(2).sum()) for k in out[0] if out[0][k].dtype.is_floating_point)
+    assert num <= (2e-3 ** 2) * den, (num / den) ** 0.5

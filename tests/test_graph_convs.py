@@ -12,7 +12,7 @@ VT = {"y": "numerical"}
 
 def _graph(n, e, seed):
     ei = synthetic_graph(n, e, seed)
-    extra = torch.tensor([[0, 1, 1, 5], [0, 2, 2, 5]])          # self loops on 0 and 5, a duplicated edge 1 -> 2
+    extra = torch.tensor([[0, 1, 1, 5, 5], [0, 2, 2, 5, 5]])    # self loops on 0 and (twice) 5, a duplicated edge 1 -> 2
     return torch.cat([ei, extra], 1)
 
 
@@ -49,6 +49,42 @@ def test_root_weight_convs_agree(kind):
     mod.load_state_dict({k[len("encoders.0.convs.0."):]: v for k, v in P.items() if k.startswith("encoders.0.convs.0.")},
                         strict=True)
     assert torch.allclose(mod(x, ei), want, atol=1e-5)
+
+
+def test_gcn_conv_follows_add_remaining_self_loops():
+    """GCNConv as torch_geometric defines it (gcn_norm -> add_remaining_self_loops -> symmetric normalisation -> sum over
+    incoming edges), written out as a per-edge loop: input self loops -- also duplicated ones -- collapse to ONE unit loop
+    per node, duplicated ordinary edges count twice, nodes without a loop get one. Checks the oracle's restatement, the
+    drop-in container and the engine's CSR operator against it."""
+    from flexynesis_b200.containers import GCNConv
+    from flexynesis_b200.engine import build_gcn_csr
+    torch.manual_seed(1)
+    n, fin, emb = 30, 4, 6
+    ei = _graph(n, 60, 2)
+    x = torch.randn(3, n, fin)
+    W, b = torch.randn(emb, fin), torch.randn(emb)
+    # literal definition
+    edges = [(s, d) for s, d in ei.t().tolist() if s != d] + [(v, v) for v in range(n)]
+    deg = [0.0] * n
+    for s, d in edges:
+        deg[d] += 1.0
+    h = x @ W.T
+    want = torch.zeros(3, n, emb)
+    for s, d in edges:
+        want[:, d] += h[:, s] / (deg[s] ** 0.5 * deg[d] ** 0.5)
+    want = want + b
+    P = {"c.lin.weight": W, "c.bias": b}
+    assert torch.allclose(gcn_conv(P, "c", x, ei), want, atol=1e-5)
+    mod = GCNConv(fin, emb)
+    mod.load_state_dict({"lin.weight": W, "bias": b})
+    assert torch.allclose(mod(x, ei), want, atol=1e-5)
+    (rp, col, w), _ = build_gcn_csr(ei, n, "cpu", "GCN")
+    got = torch.zeros(3, n, emb)
+    for v in range(n):
+        for e in range(int(rp[v]), int(rp[v + 1])):
+            got[:, v] += float(w[e]) * h[:, int(col[e])]
+    assert torch.allclose(got + b, want, atol=1e-5)
+    assert int(rp[-1]) == len(edges)
 
 
 def test_state_dict_keys_follow_pyg():

@@ -43,6 +43,8 @@ def _objective(cfg, device):
     time.sleep(0.5)                                           # long enough for every worker to be up and pulling
     if cfg.get("boom"):
         raise ValueError("boom")
+    if cfg.get("die"):
+        os._exit(3)                                           # a worker that dies without raising (OOM kill, CUDA fault)
     return (cfg["x"] ** 2, device, os.getpid())
 
 
@@ -54,6 +56,12 @@ def test_run_trials_spreads_trials_over_devices_and_keeps_order():
     assert len({r[2] for r in res}) >= 2                      # really ran in several worker processes
     with pytest.raises(RuntimeError, match="boom"):
         run_trials(_objective, [{"x": 1}, {"x": 2, "boom": True}], devices=["cpu:0"], timeout=120)
+
+
+@pytest.mark.timeout(300)
+def test_run_trials_fails_the_trial_of_a_dead_worker_instead_of_hanging():
+    with pytest.raises(RuntimeError, match="died with exit code 3"):
+        run_trials(_objective, [{"x": 1}, {"x": 2, "die": True}, {"x": 3}], devices=["cpu:0", "cpu:1"], timeout=120)
 
 
 def test_concurrent_plan():
