@@ -318,14 +318,20 @@ def test_validation_of_equal_size_cannot_alias_the_captured_training_batch():
     va = fx.SyntheticMultiOmicDataset([80, 40], 256, vt, {"c": 3}, seed=9)
     view = _DS(tr.dat, tr.ann, vt)
     cfg = {"latent_dim": 16, "hidden_dim_factor": 0.25, "supervisor_hidden_dim": 8, "lr": 5e-3}
-    out = []
+    out, hists = [], []
     for val in (None, va):
         torch.manual_seed(0)
         m = fx.DirectPred(cfg, view, ["c", "y"], device_type="gpu")
-        fx.fit.fit(m, tr, batch_size=256, epochs=4, val_dataset=val, seed=1)
+        hists.append(fx.fit.fit(m, tr, batch_size=256, epochs=4, val_dataset=val, seed=1))
         out.append({k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
-    # two runs differ by atomics-order noise that Adam's sign-like first steps amplify to ~1e-4; training three of the four
-    # steps on the validation features (the aliasing bug) moves the weights by O(lr) = 5e-3 per element
-    num = sum(float((out[0][k] - out[1][k]).double().pow(2).sum()) for k in out[0] if out[0][k].dtype.is_floating_point)
-    den = sum(float(out[0][k].double().pow(2).sum()) for k in out[0] if out[0][k].dtype.is_floating_point)
-    assert num <= (2e-3 ** 2) * den, (num / den) ** 0.5
+    # training on the validation features in three of the four steps (the aliasing bug) changes the loss curve in its
+    # first digits; two clean runs agree to fp32 summation-order noise
+    for a, b in zip(*hists):
+        assert abs(a["train_loss"] - b["train_loss"]) <= 1e-4 * abs(a["train_loss"]), (a, b)
+    # parameters: biases in front of a BatchNorm have an analytically zero gradient and random-walk by +-lr per step on
+    # rounding noise in any implementation (and drag the running means along); everything else must agree
+    skip = ("layer_1.bias", "layer_out.bias", "fusion_block.bias", "running_mean", "running_var")
+    keys = [k for k in out[0] if out[0][k].dtype.is_floating_point and not k.endswith(skip)]
+    num = sum(float((out[0][k] - out[1][k]).double().pow(2).sum()) for k in keys)
+    den = sum(float(out[0][k].double().pow(2).sum()) for k in keys)
+    assert num <= (1e-3 ** 2) * den, (num / den) ** 0.5
