@@ -121,7 +121,7 @@ SYMBOLS = [
     "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_heads_fused_ok", "fxn_heads_fwd", "fxn_heads_bwd", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
     "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn", "fxn_gcn_fwd", "fxn_gcn_bwd",
-    "fxn_merge_col_stats", "fxn_node_lin_fwd", "fxn_node_lin_bwd", "fxn_debug_gemm_trace", "fxn_debug_gemm_cta_times", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast", "fxn_dp_barrier",
+    "fxn_merge_col_stats", "fxn_merge_col_stats_big", "fxn_graph_gather", "fxn_graph_gather_ok", "fxn_node_lin_fwd", "fxn_node_lin_bwd", "fxn_debug_gemm_trace", "fxn_debug_gemm_cta_times", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast", "fxn_dp_barrier",
 ]
 
 
@@ -439,3 +439,22 @@ def dp_adam_bcast(mc_param, param_local, grad_local, m, v, begin, end, partials,
 def dp_barrier(mc_flags, local_flags, epoch, slot, world) -> None:
     check(lib.fxn_dp_barrier(C.c_void_p(mc_flags), C.c_void_p(local_flags), C.c_void_p(epoch), C.c_int(slot), C.c_int(world),
                              C.c_void_p(stream())), "fxn_dp_barrier")
+
+
+def graph_gather_ok(N: int, Cc: int) -> bool:
+    return bool(lib.fxn_graph_gather_ok(C.c_int(N), C.c_int(Cc)))
+
+
+def graph_gather(inp, B, N, Cc, csr, out=None, out_planes: "Planes" = None) -> None:
+    """csr: (rowptr, col, w[, order]) device int32 / int32 / fp32 / int32 tensors (order: nodes by decreasing row length)."""
+    order = csr[3].data_ptr() if len(csr) > 3 and csr[3] is not None else None
+    check(lib.fxn_graph_gather(C.c_void_p(inp), C.c_int(B), C.c_int(N), C.c_int(Cc), C.c_void_p(csr[0].data_ptr()),
+                               C.c_void_p(csr[1].data_ptr()), C.c_void_p(csr[2].data_ptr()), C.c_void_p(order), C.c_void_p(out),
+                               C.c_void_p(out_planes.hi_ptr if out_planes else None),
+                               C.c_void_p(out_planes.lo_ptr if out_planes else None), C.c_void_p(stream())), "fxn_graph_gather")
+
+
+def merge_col_stats_big(partials, ntiles, tile_rows, rows, cols, pld, fold, merged, scratch) -> None:
+    check(lib.fxn_merge_col_stats_big(C.c_void_p(partials), C.c_int(ntiles), C.c_int(tile_rows), c_ll(rows), C.c_int(cols),
+                                      C.c_int(pld), C.c_int(fold), C.c_void_p(merged), C.c_void_p(scratch),
+                                      C.c_void_p(stream())), "fxn_merge_col_stats_big")

@@ -694,12 +694,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             if (p.stats_mode == 2 && rows_valid > 0) {
               const float mu0 = s0 / static_cast<float>(rows_valid), mu1 = s1 / static_cast<float>(rows_valid);
               __syncwarp();
+              // all 16 staged values first (independent loads), then the arithmetic: issued one per iteration the loads cost
+              // 16 exposed shared-memory latencies per chunk, which sets the pace of short-K launches ([B * N x 256] GCN layers)
+              float2 xs[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xs[i] = lds_f2(stg_s + ((2 * i + rr) * G2_STG_LD + 2 * cp) * 4);
+#pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const int r = 2 * i + rr;
-                if (r < rows_valid) {
-                  const float2 x = lds_f2(stg_s + (r * G2_STG_LD + 2 * cp) * 4);
-                  m20 = fmaf(x.x - mu0, x.x - mu0, m20);
-                  m21 = fmaf(x.y - mu1, x.y - mu1, m21);
+                if (2 * i + rr < rows_valid) {
+                  m20 = fmaf(xs[i].x - mu0, xs[i].x - mu0, m20);
+                  m21 = fmaf(xs[i].y - mu1, xs[i].y - mu1, m21);
                 }
               }
               m20 += __shfl_xor_sync(0xffffffffu, m20, 16);
@@ -989,12 +993,14 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
   }
   const int nplanes = d->nterms == 3 ? 2 : 1;
   const int stage_bytes = nplanes * (G2_BM * G2_BK * 2 + (p.bn / pl.cg) * G2_BK * 2);
-  // Epilogue width. FXN_GEMM_EPI_WARPS=8 (opt-in; default 4) gives short-K, epilogue-bound tile-mode problems eight
+  // Epilogue width. FXN_GEMM_EPI_WARPS=8 (4 = never) gives short-K, epilogue-bound tile-mode problems eight
   // epilogue warps, provided the second set of staging buffers still leaves as many stages as there are k-blocks to
   // prefetch (or at least 3).
-  static const int epi_env = [] { const char* e = getenv("FXN_GEMM_EPI_WARPS"); return e ? atoi(e) : 4; }();
+  // Default: eight warps when K <= 4 k-blocks -- such launches ARE their epilogue (GCN layers folded to [B * N / 8 x 256]:
+  // 1389 -> 964 us, the flatten -> fc input gradient [4096 x 64000], K = 128: 577 -> 421 us; profiles/r02_timeline_cfg4_*).
+  static const int epi_env = [] { const char* e = getenv("FXN_GEMM_EPI_WARPS"); return e ? atoi(e) : 0; }();
   int ew = 4;
-  if (epi_env == 8 && !p.streamk && p.kb_total <= 16) {      // (the fix-up protocol counts four epilogue warps per CTA)
+  if (epi_env != 4 && !p.streamk && p.kb_total <= (epi_env == 8 ? 16 : 4)) {   // (the fix-up protocol counts four epilogue warps per CTA)
     int st8 = (G2_MAX_DYN_SMEM - 1024 - 2 * G2_STG_BYTES) / stage_bytes;
     if (st8 > p.stages) st8 = p.stages;
     if (st8 >= 3 || (st8 >= 2 && st8 >= p.kb_total)) { ew = 8; p.stages = st8; }

@@ -1345,6 +1345,32 @@ class GNNEngine(EngineBase):
         self.act = ACTIVATIONS[enc.act_name]
         self.wfc = self.wplanes.add_matrix("encoders.0.fc.weight")
         self.csr_in, self.csr_out = build_gcn_csr(model.edge_index, self.N, self.device, self.conv)
+
+        def by_degree(csr):      # + nodes by decreasing row length: the nodes a gather warp advances together finish together
+            deg = (csr[0][1:] - csr[0][:-1]).to(torch.int64)
+            return (*csr, torch.sort(deg, descending=True, stable=True).indices.to(torch.int32).contiguous())
+        self.gather_in, self.gather_out = by_degree(self.csr_in), by_degree(self.csr_out)
+        # wide GCN layers (emb -> emb): aggregate with the pure gather kernel, transform on the tensor cores
+        self.gemm_layers = []
+        if self.conv == "GCN" and not int(__import__("os").environ.get("FXN_GCN_FUSED", "0")):
+            for k in range(self.K):
+                fin = self.F if k == 0 else self.emb
+                if fin % 16 == 0 and self.emb % 8 == 0 and L.graph_gather_ok(self.N, fin):
+                    self.gemm_layers.append(k)
+        # The [B * N x fin] . [fin x emb] transforms are far too skinny for the tensor-core tiles (one k-block, one epilogue
+        # chunk per 256 rows: the launch is epilogue-latency bound at ~7000 cycles per tile). FOLD consecutive nodes into one
+        # GEMM row -- [B * N / f x f * fin] . blockdiag_f(W)^T -- and the same arithmetic runs as a square-ish 256-wide GEMM
+        # (the zero blocks cost tensor-core time that is free here; HBM traffic is unchanged).
+        self.fold = 8
+        self.wconv = {}
+        for k in self.gemm_layers:
+            fin = self.F if k == 0 else self.emb
+            f, pw = self.fold, f"encoders.0.convs.{k}.{self.pn[0]}"
+            ld = f * fin
+            off = self.wplanes.reserve(f * self.emb, ld)
+            for q in range(f):
+                self.wplanes.add_segment(pw, 0, self.emb, fin, fin, off + (q * self.emb) * ld + q * fin, ld)
+            self.wconv[k] = ("planes", off, f * self.emb, f * fin, ld)
         self._finish_init(0)
 
     def workspace(self, B: int) -> dict:
@@ -1368,6 +1394,19 @@ class GNNEngine(EngineBase):
         ws["dE_p"] = Planes.empty(B, Lt, dev, ld=Lp)
         ws["dD"] = f(B * N, emb)
         ws["dO"] = f(B * N, emb)
+        if self.gemm_layers:
+            rows = B * N
+            fo = self.fold
+            while rows % fo:
+                fo //= 2
+            ws["fold"] = fo
+            ws["G"] = {k: Planes.empty(rows, self.F if k == 0 else emb, dev) for k in self.gemm_layers}
+            ws["T"] = f(rows, emb)
+            ws["dO_p"] = Planes.empty(rows, emb, dev)
+            ws["tile_partials"] = f(L.stat_tiles(rows // fo) * 2 * fo * emb)
+            ws["merge_scratch"] = torch.zeros(2 * emb, dtype=torch.float64, device=dev)
+            ws["bias_bd"] = f(self.fold * emb)
+            ws["dW_bd"] = f(self.fold * emb, self.fold * emb)
         ws["x"] = None
         ws["heads"] = self.heads.workspace(B)
         self.ws[key] = ws
@@ -1386,12 +1425,27 @@ class GNNEngine(EngineBase):
             fin = self.F if k == 0 else emb
             pw, pb, pr = (f"encoders.0.convs.{k}.{n}" if n else None for n in self.pn)
             part = ws["partials"][k].data_ptr() if train else None
-            L.gcn_fwd(xin[k].data_ptr(), B, N, fin, self.csr_in[0].data_ptr(), self.csr_in[1].data_ptr(),
-                      self.csr_in[2].data_ptr(), a.p(pw), a.p(pb), emb, ws["O"][k].data_ptr(), None if pr else part)
-            if pr:      # GraphConv / SAGEConv: + root transform of the node's own features, then the statistics of O
-                L.node_lin_fwd(xin[k].data_ptr(), B, N, fin, a.p(pr), emb, ws["O"][k].data_ptr(), part)
-            if train:
-                L.merge_col_stats(ws["partials"][k].data_ptr(), B, N, rows, emb, emb, ws["merged"][k].data_ptr())
+            if k in self.gemm_layers:
+                # G = A^ X (pure gather -> operand planes), O = G W^T + b on the tensor cores with the BatchNorm tile partials
+                # in the GEMM epilogue
+                fo = ws["fold"]
+                L.graph_gather(xin[k].data_ptr(), B, N, fin, self.gather_in, out_planes=ws["G"][k])
+                Gf = Planes(ws["G"][k].hi, ws["G"][k].lo, rows // fo, fo * fin, fo * fin)
+                Wbd = self.wp(self.wconv[k])
+                Wbd = Planes(Wbd.hi, Wbd.lo, fo * emb, fo * fin, Wbd.ld, Wbd.off)       # leading fo x fo blocks of the fold-8 operand
+                ws["bias_bd"][:fo * emb].copy_(a.view(pb).repeat(fo))
+                L.gemm(rows // fo, fo * emb, fo * fin, Gf, 0, Wbd, 0, C_ptr=ws["O"][k].data_ptr(), ldc=fo * emb,
+                       bias=ws["bias_bd"].data_ptr(), colstats=ws["tile_partials"].data_ptr() if train else None, stats_mode=2)
+                if train:
+                    L.merge_col_stats_big(ws["tile_partials"].data_ptr(), L.stat_tiles(rows // fo), 128, rows // fo, emb,
+                                          fo * emb, fo, ws["merged"][k].data_ptr(), ws["merge_scratch"].data_ptr())
+            else:
+                L.gcn_fwd(xin[k].data_ptr(), B, N, fin, self.csr_in[0].data_ptr(), self.csr_in[1].data_ptr(),
+                          self.csr_in[2].data_ptr(), a.p(pw), a.p(pb), emb, ws["O"][k].data_ptr(), None if pr else part)
+                if pr:      # GraphConv / SAGEConv: + root transform of the node's own features, then the statistics of O
+                    L.node_lin_fwd(xin[k].data_ptr(), B, N, fin, a.p(pr), emb, ws["O"][k].data_ptr(), part)
+                if train:
+                    L.merge_col_stats(ws["partials"][k].data_ptr(), B, N, rows, emb, emb, ws["merged"][k].data_ptr())
             mask = None if masks is None else masks.get(f"encoders.0.dropout.{k}")
             last = k == K - 1
             kw = {}
@@ -1440,14 +1494,34 @@ class GNNEngine(EngineBase):
         for k in reversed(range(K)):
             fin = self.F if k == 0 else emb
             mask = None if masks is None else masks.get(f"encoders.0.dropout.{k}")
+            pw, pb, pr = (f"encoders.0.convs.{k}.{n}" if n else None for n in self.pn)
+            gemm_path = k in self.gemm_layers
+            out_kw = dict(dv_hi=ws["dO_p"].hi_ptr, dv_lo=ws["dO_p"].lo_ptr, ldp=emb, dbias=a.g(pb)) if gemm_path \
+                else dict(dV=ws["dO"].data_ptr(), ldd=emb)
             self.bn_backward(V=ws["O"][k].data_ptr(), ldv=emb, dOut=ws["dD"].data_ptr(), ldg=emb, rows=rows, cols=emb,
                              gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
                              saved=ws["saved"][k].data_ptr(), act=self.act, p_drop=self.p_drop,
                              mask=None if mask is None else mask.data_ptr(), ldm=emb, seed=self.seed + 7 + 131 * k,
                              seed_dev=self.noise_step.data_ptr(), pre_act=0, sums=ws["sums"][k],
                              dgamma=a.view(f"encoders.0.bns.{k}.weight", a.grad),
-                             dbeta=a.view(f"encoders.0.bns.{k}.bias", a.grad), dV=ws["dO"].data_ptr(), ldd=emb)
-            pw, pb, pr = (f"encoders.0.convs.{k}.{n}" if n else None for n in self.pn)
+                             dbeta=a.view(f"encoders.0.bns.{k}.bias", a.grad), **out_kw)
+            if gemm_path:
+                # dW = dO^T G (stream-K over the B * N rows; G is kept from the forward pass), d bias = column sums of dO (above),
+                # dX = A^T (dO W): GEMM, then the gather over the CSR by source
+                fo = ws["fold"]
+                dOf = Planes(ws["dO_p"].hi, ws["dO_p"].lo, rows // fo, fo * emb, fo * emb)
+                Gf = Planes(ws["G"][k].hi, ws["G"][k].lo, rows // fo, fo * fin, fo * fin)
+                Wbd = self.wp(self.wconv[k])
+                Wbd = Planes(Wbd.hi, Wbd.lo, fo * emb, fo * fin, Wbd.ld, Wbd.off)
+                dWbd = ws["dW_bd"][:fo * emb, :fo * fin]
+                L.gemm(fo * emb, fo * fin, rows // fo, dOf, 1, Gf, 1, C_ptr=ws["dW_bd"].data_ptr(), ldc=ws["dW_bd"].stride(0),
+                       splitk=-1)
+                # the diagonal blocks of dO_f^T G_f are the fold partial sums of dW (the off-diagonal blocks pair different nodes)
+                torch.sum(torch.diagonal(dWbd.reshape(fo, emb, fo, fin), dim1=0, dim2=2), dim=-1, out=a.view(pw, a.grad))
+                if k > 0:
+                    L.gemm(rows // fo, fo * fin, fo * emb, dOf, 0, Wbd, 1, C_ptr=ws["T"].data_ptr(), ldc=fo * fin)
+                    L.graph_gather(ws["T"].data_ptr(), B, N, fin, self.gather_out, out=ws["dD"].data_ptr())
+                continue
             dX = ws["dD"].data_ptr() if k > 0 else None
             L.gcn_bwd(xin[k].data_ptr(), ws["dO"].data_ptr(), B, N, fin, emb, self.csr_in, self.csr_out,
                       a.p(pw), a.g(pw), a.g(pb), dX)

@@ -301,6 +301,23 @@ int fxn_node_lin_bwd(const float* X, const float* dO, int B, int N, int Fin, int
 int fxn_merge_col_stats(const float* partials, int ntiles, int tile_rows, long long rows, int cols, int pld,
                         float* merged, void* stream);
 
+/* Pure neighbour aggregation out[b, v, :] = sum_{e in CSR row v} w_e * in[b, col_e, :] over [B, N, C] fp32 node features
+ * (C % 16 == 0, N * 64 bytes within shared memory: fxn_graph_gather_ok). Output as fp32 (`out`) or as bf16 operand planes
+ * (out_hi / out_lo, ld = C). With it a GCNConv layer (torch_geometric; flexynesis/modules.py:221-226, :254) runs as
+ * G = A^ X (gather) ; O = G W^T + b (fxn_gemm) and its backward as T = dO W (fxn_gemm) ; dX = A^T T (gather over the CSR by
+ * source) ; dW = dO^T G (fxn_gemm): the per-node linear maps are tensor-core GEMMs over B * N rows.
+ * `order` (optional, may be NULL): a permutation of the N nodes, e.g. by decreasing CSR row length; nodes are processed in
+ * that order so that the nodes a warp advances together have similar degrees. The result does not depend on it. */
+int fxn_graph_gather_ok(int N, int C);
+int fxn_graph_gather(const float* in, int B, int N, int C, const int* rowptr, const int* col, const float* w,
+                     const int* order, float* out, void* out_hi, void* out_lo, void* stream);
+/* fxn_merge_col_stats for tens of thousands of tiles (the 128-row tile partials of a [B * N x C] fxn_gemm output):
+ * two parallel passes with double-precision atomics; scratch = 2 * cols doubles (zeroed by the call). fold > 1: the GEMM
+ * ran on the matrix viewed as [rows x fold * cols] (fold consecutive nodes per GEMM row, block-diagonal weights), so
+ * partials has fold * cols columns and column q * cols + c belongs to channel c; `rows` counts the folded rows. */
+int fxn_merge_col_stats_big(const float* partials, int ntiles, int tile_rows, long long rows, int cols, int pld, int fold,
+                            float* merged, double* scratch, void* stream);
+
 /* ---- step policy ----
  * clip_grad_norm_(params, max_norm) + Adam on flat arenas (flexynesis/main.py:216-217, direct_pred.py:135-144).
  * grads are multiplied by grad_scale (1/world_size after a sum all-reduce) before the norm. *step_counter (int64)

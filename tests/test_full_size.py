@@ -6,7 +6,8 @@ import pytest
 import torch
 
 from oracle.restatement import Spec, synthetic_graph
-from test_gpu_parity import (Report, build_model, compare_step, masks_from_noise, oracle_reference, sync_state, to_cuda)
+from test_gpu_parity import (Report, build_model, compare_step, gnn_oracle_steps, masks_from_noise, oracle_reference,
+                             sync_state, to_cuda)
 
 pytestmark = pytest.mark.gpu
 VT = {"y": "numerical", "c": "categorical", "e": "numerical", "t": "numerical"}
@@ -113,7 +114,7 @@ def test_full_size_gnn_matches_oracle():
     spec = Spec(model="GNN", input_dims=[1], latent_dim=128, supervisor_hidden_dim=32, variables=["y"], variable_types=VT,
                 node_count=2000, node_embedding_dim=32, num_convs=2, activation="relu")
     edge_index = synthetic_graph(2000, 20000, 0)
-    P0, batch, steps, _ = oracle_reference(spec, 512, 1e-3, steps=1, edge_index=edge_index)
+    P0, batch, steps = gnn_oracle_steps(spec, 512, 1e-3, 1, edge_index)
     model = build_model(spec, batch, 1e-3, P0, edge_index)
     model.train()
     rep = Report()
