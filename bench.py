@@ -474,7 +474,7 @@ def build_data_parallel(w, prob, dev, world, use_nccl):
     return model, (GradAllReduce(world) if world > 1 else None), ("nccl" if world > 1 else "single"), ""
 
 
-def dp_consistency(model, allreduce, world, dev):
+def dp_consistency(model, allreduce, world, dev, batch=None):
     """After the timed steps: (1) every rank holds bit-identical parameters; (2) ONE more optimizer step through the
     multicast kernels equals, on every rank's slice, the same step through an NCCL all-reduce + the single-GPU optimizer
     kernel (same gradients, same Adam state) to fp32 rounding."""
@@ -495,7 +495,7 @@ def dp_consistency(model, allreduce, world, dev):
         state = [t.clone() for t in (a.flat, a.exp_avg, a.exp_avg_sq, a.step)]
         a.grad.copy_(grad)
         torch.cuda.synchronize(); dist.barrier()
-        allreduce.step(1e-3)
+        allreduce.step(1e-3, pull_all=True)           # (random gradients in the arena, not a backward pass of the GEMMs)
         torch.cuda.synchronize(); dist.barrier()
         got = a.flat.clone()
         for dst, src in zip((a.flat, a.exp_avg, a.exp_avg_sq, a.step), state):
@@ -517,6 +517,35 @@ def dp_consistency(model, allreduce, world, dev):
             dst.copy_(src)
         eng.wplanes.refresh()
         torch.cuda.synchronize(); dist.barrier()
+    if getattr(allreduce, "rs", None) is not None and batch is not None:
+        # (3) one whole training step with the reduce-scatter fused into the weight-gradient GEMMs (what the timed steps ran)
+        # against the same step with every gradient pulled through the switch afterwards: same state, same dropout counter
+        bufs = list(model.buffers())
+        keep = [t.clone() for t in (a.flat, a.exp_avg, a.exp_avg_sq, a.step, eng.noise_step)] + [b.clone() for b in bufs]
+
+        def restore():
+            for dst, src in zip([a.flat, a.exp_avg, a.exp_avg_sq, a.step, eng.noise_step] + bufs, keep):
+                dst.copy_(src)
+            eng.wplanes.refresh()
+            torch.cuda.synchronize(); dist.barrier()
+
+        def one_step(fused):
+            allreduce.rs.enabled = fused
+            g, y = model._split_batch(batch)
+            eng.forward_backward(g, y, None)
+            allreduce.step(1e-3, pull_all=not fused)
+            torch.cuda.synchronize(); dist.barrier()
+            out = a.flat.clone()
+            restore()
+            return out
+        n_ranges = len(allreduce.rs.merged_ranges())
+        covered = sum(hi - lo for lo, hi in allreduce.rs.merged_ranges())
+        p_fused, p_pull = one_step(True), one_step(False)
+        allreduce.rs.enabled = True
+        t = torch.stack([(p_fused - p_pull).abs().max(), (p_fused - keep[0]).abs().max()])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rec.update({"fused_reduce_scatter": {"gemm_ranges": n_ranges, "arena_fraction": covered / a.numel,
+                                             "step_vs_pull_step_max_abs_diff": float(t[0]), "update_scale": float(t[1])}})
     return rec
 
 
@@ -692,7 +721,7 @@ def run_b200(args, w):
         sustained = {"value": world * B / (ms_sus * 1e-3), "unit": "samples/s", "ms_per_step": ms_sus, "steps": n_sus,
                      "seconds": n_sus * ms_sus * 1e-3, "clocks": sampler2.stop() if rank == 0 else None}
     # ---------------- data-parallel consistency (N > 1) ----------------
-    dp_check = dp_consistency(model, allreduce, world, dev) if world > 1 else None
+    dp_check = dp_consistency(model, allreduce, world, dev, step.batch) if world > 1 else None
     # ---------------- other BASELINE configs at this GPU count + the reference's default mini-batch regime ----------------
     also = {}
     if not args.quick:

@@ -37,7 +37,44 @@ class GemmDesc(C.Structure):
         ("max_groups", C.c_int),
         ("fix_ws", C.c_void_p), ("fix_ws_bytes", c_ll),
         ("fix_flags", C.c_void_p), ("fix_flags_count", c_ll),
+        ("rs_world", C.c_int), ("rs_rank", C.c_int), ("rs_per", c_ll), ("rs_base", C.c_void_p), ("rs_inbox", C.c_void_p),
     ]
+
+
+class ReduceScatterContext:
+    """Data-parallel jobs (parallel.NvlsDataParallel): while one of these is installed as `_lib.RS`, every weight-gradient
+    GEMM whose plain stream-K output covers a contiguous, 4-aligned range of the gradient arena sends the reductions that
+    belong to another rank's slice straight into that rank's inbox arena (fxn_gemm_desc.rs_*), and records the range so that
+    fxn_dp_reduce_sumsq knows where own + inbox replaces the pull through the switch."""
+
+    def __init__(self, world, rank, per, base_ptr, numel, inbox_ptrs):
+        self.world, self.rank, self.per, self.base, self.numel = int(world), int(rank), int(per), int(base_ptr), int(numel)
+        self.inbox = (C.c_void_p * self.world)(*[int(p) for p in inbox_ptrs])
+        self.ranges = set()
+        self.enabled = True
+        self.min_elems = 1 << 18
+
+    def claim(self, C_ptr, M, N, ldc):
+        """(element offset) if this output can take the fused path, else None"""
+        if not self.enabled or ldc != N:
+            return None
+        off = (int(C_ptr) - self.base) // 4
+        n = int(M) * int(N)
+        if (int(C_ptr) - self.base) % 16 or off < 0 or off + n > self.numel or n % 4 or off + n >= 1 << 31:
+            return None
+        return off
+
+    def merged_ranges(self):
+        out = []
+        for lo, hi in sorted(self.ranges):
+            if out and lo <= out[-1][1]:
+                out[-1][1] = max(out[-1][1], hi)
+            else:
+                out.append([lo, hi])
+        return out
+
+
+RS = None        # the installed ReduceScatterContext (one data-parallel engine per process)
 
 
 class BnFwdDesc(C.Structure):
@@ -232,6 +269,16 @@ def gemm(M, N, K, a: Planes, a_mn, b: Planes, b_mn, *, C_ptr=None, ldc=0, bias=N
     if fix is not None:
         d.fix_ws, d.fix_ws_bytes = fix.ws.data_ptr(), fix.ws.numel() * 4
         d.fix_flags, d.fix_flags_count = fix.flags.data_ptr(), fix.flags.numel()
+    if (RS is not None and C_ptr and splitk < 0 and out is None and colstats is None and not epi_act and not accumulate
+            and mse_x is None and bias is None):
+        off = RS.claim(C_ptr, M, N, ldc)
+        # only launches the planner runs as stream-K reductions anyway (the large weight gradients): forcing that mode on the
+        # small ones cost more than their exchange saves
+        if off is not None and int(M) * int(N) >= RS.min_elems and \
+                gemm_plan(M, N, K, nterms, b_mn, plain_c=True, block_n=block_n, max_groups=max_groups)["streamk"] == 1:
+            d.rs_world, d.rs_rank, d.rs_per, d.rs_base = RS.world, RS.rank, RS.per, RS.base
+            d.rs_inbox = C.cast(RS.inbox, C.c_void_p)
+            RS.ranges.add((off, off + int(M) * int(N)))
     check(lib.fxn_gemm(C.byref(d), C.c_void_p(stream())), "fxn_gemm")
 
 
@@ -422,18 +469,31 @@ def merge_col_stats(partials, ntiles, tile_rows, rows, cols, pld, merged) -> Non
                                   C.c_int(pld), C.c_void_p(merged), C.c_void_p(stream())), "fxn_merge_col_stats")
 
 
-def dp_reduce_sumsq(mc_grad, grad_local, begin, end, scale, mc_partials, rank, scratch16, step) -> None:
+def dp_reduce_sumsq(mc_grad, grad_local, begin, end, scale, mc_partials, rank, scratch16, step, sync=None, peers=None,
+                    inbox=None, ranges=None) -> None:
+    """sync: None (the caller places the barrier) or (mc_flags, local_flags, epoch48, slot, world): barrier inside the kernel.
+    peers: None (in-switch reduction through mc_grad) or the list of every rank's gradient-arena pointer (peer loads).
+    inbox + ranges: this rank's inbox arena and the <= 8 element ranges [lo, hi) whose reduce-scatter already happened inside
+    the weight-gradient GEMMs (ReduceScatterContext): there the sum is grad_local + inbox, and the inbox is cleared."""
+    mc, lf, ep, slot, world = sync if sync is not None else (None, None, None, 0, 1)
+    parr = (C.c_void_p * len(peers))(*peers) if peers else None
+    nr = len(ranges) if (ranges and inbox) else 0
+    rarr = (c_ll * (2 * nr))(*[int(v) for r in ranges for v in r]) if nr else None
     check(lib.fxn_dp_reduce_sumsq(C.c_void_p(mc_grad), C.c_void_p(grad_local), c_ll(begin), c_ll(end), C.c_float(scale),
                                   C.c_void_p(mc_partials), C.c_int(rank), C.c_void_p(scratch16), C.c_void_p(step),
-                                  C.c_void_p(stream())), "fxn_dp_reduce_sumsq")
+                                  C.c_void_p(mc), C.c_void_p(lf), C.c_void_p(ep), C.c_int(slot), C.c_int(world),
+                                  parr, C.c_int(len(peers) if peers else 0), C.c_void_p(inbox if nr else None), rarr,
+                                  C.c_int(nr), C.c_void_p(stream())), "fxn_dp_reduce_sumsq")
 
 
 def dp_adam_bcast(mc_param, param_local, grad_local, m, v, begin, end, partials, world, lr, max_norm, step, norm_out,
-                  beta1=0.9, beta2=0.999, eps=1e-8) -> None:
+                  beta1=0.9, beta2=0.999, eps=1e-8, sync=None) -> None:
+    mc, lf, ep, slot, _ = sync if sync is not None else (None, None, None, 0, 1)
     check(lib.fxn_dp_adam_bcast(C.c_void_p(mc_param), C.c_void_p(param_local), C.c_void_p(grad_local), C.c_void_p(m),
                                 C.c_void_p(v), c_ll(begin), c_ll(end), C.c_void_p(partials), C.c_int(world), C.c_float(lr),
                                 C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(max_norm), C.c_void_p(step),
-                                C.c_void_p(norm_out), C.c_void_p(stream())), "fxn_dp_adam_bcast")
+                                C.c_void_p(norm_out), C.c_void_p(mc), C.c_void_p(lf), C.c_void_p(ep), C.c_int(slot),
+                                C.c_void_p(stream())), "fxn_dp_adam_bcast")
 
 
 def dp_barrier(mc_flags, local_flags, epoch, slot, world) -> None:

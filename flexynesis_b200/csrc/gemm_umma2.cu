@@ -62,7 +62,25 @@ struct Gemm2Args {
   int epi_variant;        // index of the specialised epilogue loop for interior chunks, -1 = generic only
   float* fix_ws;          // streamk == 2: [groups][CG][4 quarters][bn / 32][8][32 lanes][4] fp32 partial accumulators
   unsigned* fix_flags;    // streamk == 2: [2][groups]: contributor arrivals, owner departures (zero between launches)
+  // Data-parallel reduce-scatter fused into the stream-K reductions (rs_world > 1): C lies in this rank's gradient arena
+  // (base rs_base), the arena is cut into rs_world slices of rs_per elements (the last one takes the remainder), and a
+  // reduction whose target element belongs to another rank's slice goes to THAT rank's inbox arena over NVLink instead
+  // of into the local C. The exchange rides under the GEMM's main loop; csrc/dp.cu adds own + inbox afterwards.
+  float* rs_inbox[8];
+  const float* rs_base;
+  unsigned rs_per;
+  int rs_world, rs_rank;
 };
+
+// where the reduction for local element address `cp` has to go (rs_world > 1): the local C for this rank's own slice, the
+// owner's inbox otherwise. per is a multiple of 4 and every arena offset below 2^31, so a 16-byte aligned float4 never
+// straddles two slices.
+__device__ __forceinline__ float* rs_target(const Gemm2Args& p, float* cp) {
+  const unsigned off = static_cast<unsigned>(cp - p.rs_base);
+  int owner = static_cast<int>(off / p.rs_per);
+  owner = owner < p.rs_world ? owner : p.rs_world - 1;
+  return owner == p.rs_rank ? cp : p.rs_inbox[owner] + off;
+}
 
 // ---- PTX pieces that differ between cta_group::1 and ::2 ----
 template <int CG> __device__ __forceinline__ void g2_tmem_alloc(uint32_t* dst, uint32_t ncols) {
@@ -258,6 +276,21 @@ __device__ __forceinline__ void epi_red4(const Gemm2Args& p, uint32_t stg_s, int
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = lds_f4(stg_s + ((4 * i + r4) * G2_STG_LD + c4) * 4);
   float* cp = p.C + static_cast<long long>(mbase + r4) * p.ldc + col0 + c4;
+  if (p.rs_world > 1) {
+    // one owner for all eight rows of this lane (the usual case): one address translation; otherwise row by row
+    float* first = rs_target(p, cp);
+    float* last = rs_target(p, cp + static_cast<long long>(28) * p.ldc);
+    const bool uniform = (first - cp) == (last - (cp + static_cast<long long>(28) * p.ldc));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (4 * i + r4 < rows_valid) {
+        float* row = cp + static_cast<long long>(4 * i) * p.ldc;
+        float* dst = uniform ? row + (first - cp) : rs_target(p, row);
+        red_add_f4(dst, fmaf(v[i].x, alpha, b0), fmaf(v[i].y, alpha, b1), fmaf(v[i].z, alpha, b2), fmaf(v[i].w, alpha, b3));
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if (4 * i + r4 < rows_valid)
@@ -340,8 +373,13 @@ __device__ __forceinline__ void epi_rows(const Gemm2Args& p, const EpiRowCtx& cx
     if (cmode != 0 && rok) {
       float* cp_ = cptr + static_cast<long long>(2 * i) * p.ldc;
       if (cmode == 3) {
-        if (ok0) atomicAdd(cp_, x.x);
-        if (ok1) atomicAdd(cp_ + 1, x.y);
+        if (p.rs_world > 1) {
+          if (ok0) atomicAdd(rs_target(p, cp_), x.x);
+          if (ok1) atomicAdd(rs_target(p, cp_ + 1), x.y);
+        } else {
+          if (ok0) atomicAdd(cp_, x.x);
+          if (ok1) atomicAdd(cp_ + 1, x.y);
+        }
       } else if (!RT || (ok1 && cx.c_vec2)) {
         float2 o = x;
         if constexpr (!RT && CMODE == 2 && !MSE) { o.x += xt[i].x; o.y += xt[i].y; }
@@ -556,7 +594,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const bool has_contrib = fix && owner && sg.kb0 > 0;
       const bool add_bias = p.bias != nullptr && (fix ? owner : sg.kb0 == 0);
       // a stream-K segment that covers the whole K range of its tile is the only contributor: plain stores into the zeroed C
-      const bool whole_tile = sg.kb0 == 0 && sg.kb1 == p.kb_total;
+      // (with the fused reduce-scatter every tile goes through the reductions: a plain store could not reach a peer's inbox)
+      const bool whole_tile = sg.kb0 == 0 && sg.kb1 == p.kb_total && p.rs_world <= 1;
       const bool atomic_out = p.streamk == 1 && !whole_tile;
       // Workspace slot g = the partial accumulator of group g's (single) contributor segment, this warp's part being
       // [rank][quarter][chunk][8][32 lanes][4] floats in register order; flag word g counts the epilogue warps of group g
@@ -800,7 +839,8 @@ struct Plan { int cg, bn, stages, streamk, groups, tiles_m, tiles_n; };
 //   mode 1  stream-K, vector reductions into a zeroed plain fp32 C
 //   mode 2  stream-K with fix-up through a workspace (any epilogue; needs fxn_gemm_desc.fix_ws)
 // group_limit > 0 caps the number of CTA groups (the engine splits the SMs between GEMMs that run concurrently).
-Plan make_plan(int M, int N, int K, int nterms, int b_mn, bool plain_c, int force_bn, bool fix_ok = false, int group_limit = 0) {
+Plan make_plan(int M, int N, int K, int nterms, int b_mn, bool plain_c, int force_bn, bool fix_ok = false, int group_limit = 0,
+               bool only_reductions = false) {
   const int nplanes = nterms == 3 ? 2 : 1;
   const int kb_total = (K + G2_BK - 1) / G2_BK;
   const int cg = M > G2_BM ? 2 : 1;
@@ -827,7 +867,8 @@ Plan make_plan(int M, int N, int K, int nterms, int b_mn, bool plain_c, int forc
     const double t_mma = nterms * 4.0 * (bn / 2.0) + 90.0;
     const double t_epi = EPI_CHUNK * ((bn + 31) / 32);
     for (int mode = 0; mode < 3; ++mode) {
-      if (mode == 1 && (!plain_c || kb_total < 4)) continue;
+      if (only_reductions && mode != 1) continue;              // fused reduce-scatter: stream-K reductions, whatever K
+      if (mode == 1 && (!plain_c || (kb_total < 4 && !only_reductions))) continue;
       if (mode == 2 && (plain_c || !fix_ok || no_fix || kb_total < 8 || bn % 32 != 0)) continue;
       if (mode == 0 && force_sk && plain_c && kb_total >= 4) continue;
       int groups;
@@ -906,7 +947,25 @@ int gemm2_dispatch(const fxn_gemm_desc* d, cudaStream_t stream) {
   p.nterms = d->nterms;
   const bool plain_c = (d->splitk < 0 || d->splitk > 1) && d->C && !d->c_hi && !d->colstats && !d->epi_act && !d->accumulate && !d->mse_x;
   const bool fix_ok = d->fix_ws != nullptr && d->fix_flags != nullptr;
-  Plan pl = make_plan(d->M, d->N, d->K, d->nterms, p.b_mn, plain_c, d->block_n, fix_ok, d->max_groups);
+  const bool rs = d->rs_world > 1;
+  if (rs) {
+    if (!plain_c) return set_error(FXN_ERR_UNSUPPORTED, "fxn_gemm: the fused reduce-scatter needs a plain fp32 output with splitk < 0");
+    if (d->rs_world > 8 || d->rs_rank < 0 || d->rs_rank >= d->rs_world || !d->rs_base || !d->rs_inbox || d->rs_per <= 0 ||
+        d->rs_per % 4 || d->rs_per >= (1LL << 31))
+      return set_error(FXN_ERR_ARG, "fxn_gemm: bad reduce-scatter arguments (2..8 ranks, slice a multiple of 4 elements)");
+    const long long off0 = d->C - d->rs_base;
+    if (off0 < 0 || off0 + static_cast<long long>(d->M - 1) * d->ldc + d->N >= (1LL << 31))
+      return set_error(FXN_ERR_ARG, "fxn_gemm: C must lie in the first 2^31 elements of the reduce-scatter arena");
+    for (int r = 0; r < d->rs_world; ++r) {
+      if (r != d->rs_rank && !d->rs_inbox[r]) return set_error(FXN_ERR_ARG, "fxn_gemm: missing peer inbox");
+      p.rs_inbox[r] = d->rs_inbox[r];
+    }
+    p.rs_base = d->rs_base;
+    p.rs_per = static_cast<unsigned>(d->rs_per);
+    p.rs_world = d->rs_world;
+    p.rs_rank = d->rs_rank;
+  }
+  Plan pl = make_plan(d->M, d->N, d->K, d->nterms, p.b_mn, plain_c, d->block_n, fix_ok, d->max_groups, rs);
   if (pl.stages < 1) return set_error(FXN_ERR_ARG, "fxn_gemm: tile does not fit in shared memory");
   if (pl.streamk == 2) {
     // one slot per group: [cg][4][ceil(bn / 32)][1024] floats; two flag words per group

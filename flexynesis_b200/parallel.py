@@ -141,36 +141,67 @@ class NvlsDataParallel:
         self.flags = symm_mem.empty(16, dtype=torch.int32, device=a.device)
         self.flags.zero_()
         self.h_flags = symm_mem.rendezvous(self.flags, group)
-        self.epoch = torch.zeros(16, dtype=torch.int32, device=a.device)
-        self.host_barriers = bool(int(__import__("os").environ.get("FXN_DP_HOST_BARRIERS", "0"))) or not self.h_flags.multicast_ptr
+        self.epoch = torch.zeros(48, dtype=torch.int32, device=a.device)      # [0..15] epochs, [16..47] kernel scratch
+        env = __import__("os").environ
+        self.host_barriers = bool(int(env.get("FXN_DP_HOST_BARRIERS", "0"))) or not self.h_flags.multicast_ptr
+        self.fused_barriers = bool(int(env.get("FXN_DP_FUSED_BARRIERS", "0")))       # barriers 1 and 2 inside their kernels
+        # (measured at 2 ranks: no gain over the stand-alone barrier kernels -- the wait is rank skew, not launch overhead)
+        # gradient reduce-scatter: multimem.ld_reduce in the switch (default) or peer loads added in rank order (<= 8 ranks)
+        mode = env.get("FXN_DP_REDUCE", "multimem")     # at 2 ranks: multimem 30 us, peer loads 39 us for the 4.3 MB slice
+        self.peer_grads = [int(p) for p in self.h_grad.buffer_ptrs] if mode == "p2p" else None
+        # Reduce-scatter fused into the weight-gradient GEMMs (opt-in: FXN_DP_FUSED_RS=1, <= 8 ranks): every rank owns an inbox
+        # arena; a GEMM's stream-K reductions for elements of another rank's slice travel over NVLink into that rank's inbox
+        # while the GEMM runs, and the reduce kernel adds own + inbox instead of pulling through the switch. Correct (bench
+        # dp_check.fused_reduce_scatter) but NOT faster on this box: the remote reductions slow the GEMM by ~9 us and the
+        # reduce kernel does not get shorter (its time is not set by the bytes it pulls) -- 0.461 vs 0.456 ms per step at
+        # 2 ranks, profiles/r02_dp_timeline_cfg2_n2_fused_rs.log. Kept as an experiment switch.
+        self.rs = None
+        if self.world <= 8 and bool(int(env.get("FXN_DP_FUSED_RS", "0"))) and a.numel < (1 << 31):
+            self.inbox = symm_mem.empty(a.numel, dtype=torch.float32, device=a.device)
+            self.inbox.zero_()
+            self.h_inbox = symm_mem.rendezvous(self.inbox, group)
+            self.rs = L.ReduceScatterContext(self.world, self.rank, per, a.grad.data_ptr(), a.numel,
+                                             [int(p) for p in self.h_inbox.buffer_ptrs])
+            L.RS = self.rs
         # make every rank start from rank 0's parameters
         dist.broadcast(a.flat, 0, group=group)
         eng.wplanes.refresh()
         torch.cuda.synchronize()
         self.h_flat.barrier(channel=0)
 
-    def _barrier(self, handle):
+    def _barrier(self, handle, slot=None):
+        slot = 2 if slot is None else slot
         if self.host_barriers:                           # torch symmetric-memory barrier, enqueued by the host (not capturable)
             handle.barrier(channel=0)
         else:                                            # one device thread per rank, in stream order (capturable)
-            self.L.dp_barrier(self.h_flags.multicast_ptr, self.flags.data_ptr(), self.epoch.data_ptr(), 0, self.world)
+            self.L.dp_barrier(self.h_flags.multicast_ptr, self.flags.data_ptr(), self.epoch.data_ptr(), slot, self.world)
+
+    def _sync(self, slot):
+        return (self.h_flags.multicast_ptr, self.flags.data_ptr(), self.epoch.data_ptr(), slot, self.world)
 
     @property
     def capturable(self) -> bool:
         return not self.host_barriers
 
-    def step(self, lr: float, max_norm: float = 1.0):
+    def step(self, lr: float, max_norm: float = 1.0, pull_all: bool = False):
         """Collective: call on every rank after its backward pass has been queued on the current stream. With the
         in-stream barriers the whole sequence is plain kernel launches and can be captured in the same CUDA graph as the
-        backward pass."""
+        backward pass. pull_all: the gradient arena was filled by something other than this engine's backward pass (tests,
+        bench.dp_consistency): pull every element through the switch, ignore the ranges the GEMMs reduce-scatter."""
         L, a = self.L, self.eng.arena
-        self._barrier(self.h_grad)                       # every rank's gradients are complete and visible
+        dev_sync = not self.host_barriers and self.fused_barriers
+        if not dev_sync:
+            self._barrier(self.h_grad)                   # every rank's gradients are complete and visible
         L.dp_reduce_sumsq(self.h_grad.multicast_ptr, a.grad.data_ptr(), self.begin, self.end, 1.0 / self.world,
-                          self.h_part.multicast_ptr, self.rank, self.scratch.data_ptr(), a.step.data_ptr())
-        self._barrier(self.h_part)                       # all partial norms have landed everywhere
+                          self.h_part.multicast_ptr, self.rank, self.scratch.data_ptr(), a.step.data_ptr(),
+                          sync=self._sync(0) if dev_sync else None, peers=self.peer_grads,
+                          inbox=self.inbox.data_ptr() if self.rs is not None else None,
+                          ranges=self.rs.merged_ranges() if (self.rs is not None and not pull_all) else None)
+        if not dev_sync:
+            self._barrier(self.h_part)                   # all partial norms have landed everywhere
         L.dp_adam_bcast(self.h_flat.multicast_ptr, a.flat.data_ptr(), a.grad.data_ptr(), a.exp_avg.data_ptr(),
                         a.exp_avg_sq.data_ptr(), self.begin, self.end, self.partials.data_ptr(), self.world, lr, max_norm,
-                        a.step.data_ptr(), a.grad_norm.data_ptr())
+                        a.step.data_ptr(), a.grad_norm.data_ptr(), sync=self._sync(1) if dev_sync else None)
         self._barrier(self.h_flat)                       # all slices of the new parameters have landed
         self.eng.wplanes.refresh()
 

@@ -93,6 +93,17 @@ typedef struct fxn_gemm_desc {
   int max_groups;
   float* fix_ws; long long fix_ws_bytes;
   void* fix_flags; long long fix_flags_count;
+  /* Data-parallel weight gradients (rs_world = 2..8; 0 or 1 = off; no reference counterpart, pl.Trainer(devices=1),
+   * flexynesis/main.py:223): the reduce-scatter of the gradient is fused into the GEMM. C must be a plain fp32 stream-K
+   * output (splitk < 0) inside this rank's gradient arena, which starts at rs_base and is cut into rs_world slices of
+   * rs_per elements (a multiple of 4; the last slice takes the remainder). Reductions for elements of this rank's own
+   * slice go to C as usual; those for another rank's slice are issued over NVLink into rs_inbox[owner] + (element offset
+   * from rs_base), the owner's peer-mapped inbox arena (HOST array of rs_world device pointers; [rs_rank] is ignored). The
+   * owner's total for its slice is C + inbox once every rank's GEMM has finished (fxn_dp_reduce_sumsq adds them). */
+  int rs_world, rs_rank;
+  long long rs_per;
+  const float* rs_base;
+  float* const* rs_inbox;
 } fxn_gemm_desc;
 int fxn_gemm(const fxn_gemm_desc* d, void* stream);
 /* Debug aid: with FXN_GEMM_TRACE=1 in the environment the persistent kernel stamps clock64 at its pipeline milestones
@@ -330,13 +341,25 @@ int fxn_clip_adam_step(float* params, const float* grads, float* exp_avg, float*
  * arena slice [begin, end) (multiples of 4 elements).
  * fxn_dp_reduce_sumsq: grad_local[slice] = scale * sum over ranks (multimem.ld_reduce), its squared norm is stored into
  *   slot `rank` of the symmetric partials array on every rank (multimem.st); *step_counter += 1. scratch16: 16 zeroed bytes.
- * -- callers place a system-wide barrier here --
- * fxn_dp_adam_bcast: global-norm clip + Adam on the slice, new parameters multicast into every rank's arena. */
+ * -- a system-wide barrier belongs here --
+ * fxn_dp_adam_bcast: global-norm clip + Adam on the slice, new parameters multicast into every rank's arena.
+ * Barriers: with mc_flags != NULL each call starts with a barrier between the ranks INSIDE its kernel (before touching any
+ * peer data): mc_flags / local_flags as for fxn_dp_barrier, epoch48 a local device uint32[48] zeroed once ([0..15] epochs,
+ * [16..47] scratch), `slot` a flag slot no other call site uses. With mc_flags == NULL the caller provides the barriers.
+ * peer_grads (HOST array of npeers <= 8 device pointers, rank order, may be NULL): every rank's gradient arena as mapped
+ * into this process; when given the W copies are fetched with plain peer loads and added in rank order instead of
+ * multimem.ld_reduce on mc_grad.
+ * inbox / fused_ranges (HOST array of nranges <= 8 pairs [lo, hi) of element offsets, 4-aligned; may be NULL / 0): ranges of
+ * the arena whose reduce-scatter already happened inside the weight-gradient GEMMs (fxn_gemm_desc.rs_*): there the slice's
+ * sum is grad_local + inbox (both local), and the inbox is cleared for the next step. */
 int fxn_dp_reduce_sumsq(const void* mc_grad, float* grad_local, long long begin, long long end, float scale, void* mc_partials,
-                        int rank, void* scratch16, long long* step_counter, void* stream);
+                        int rank, void* scratch16, long long* step_counter, void* mc_flags, const void* local_flags,
+                        void* epoch48, int slot, int world, const float* const* peer_grads, int npeers, float* inbox,
+                        const long long* fused_ranges, int nranges, void* stream);
 int fxn_dp_adam_bcast(void* mc_param, const float* param_local, const float* grad_local, float* exp_avg, float* exp_avg_sq,
                       long long begin, long long end, const float* partials, int world, float lr, float beta1, float beta2,
-                      float eps, float max_norm, const long long* step_counter, float* norm_out, void* stream);
+                      float eps, float max_norm, const long long* step_counter, float* norm_out, void* mc_flags,
+                      const void* local_flags, void* epoch48, int slot, void* stream);
 /* Barrier between the ranks of a data-parallel job, executed in stream order by one device thread per rank: mc_flags is
  * the multicast address of a symmetric uint32[16] array (zeroed once), local_flags this rank's copy, epoch a local device
  * uint32[16] (zeroed once). Every rank must issue the same sequence of barriers. Capturable in a CUDA graph. */
