@@ -90,6 +90,7 @@ class BnFwdDesc(C.Structure):
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldp", c_ll),
         ("saved", C.c_void_p),
         ("stat_rows", c_ll),
+        ("keep_bits", C.c_void_p),
     ]
 
 
@@ -105,6 +106,7 @@ class BnBwdDesc(C.Structure):
         ("dv_hi", C.c_void_p), ("dv_lo", C.c_void_p), ("ldp", c_ll),
         ("grad_scale", C.c_float), ("accumulate_affine", C.c_int),
         ("stat_rows", c_ll), ("prezeroed", C.c_int), ("phase", C.c_int),
+        ("keep_bits", C.c_void_p),
     ]
 
 
@@ -155,7 +157,7 @@ lib = _load()
 SYMBOLS = [
     "fxn_version", "fxn_last_error", "fxn_launch_count", "fxn_reset_launch_count", "fxn_split_planes", "fxn_gemm",
     "fxn_gemm_stat_tiles", "fxn_gemm_plan", "fxn_gemm_fix_ws_bytes", "fxn_gemm_fix_flag_words", "fxn_bn_act_fwd", "fxn_bn_act_bwd", "fxn_col_stats", "fxn_head_out_fwd", "fxn_head_out_bwd",
-    "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_heads_fused_ok", "fxn_heads_fwd", "fxn_heads_bwd", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
+    "fxn_cox_fwd", "fxn_cox_max_rows", "fxn_cox_fwd_ws", "fxn_cox_ws_floats", "fxn_heads_fused_ok", "fxn_heads_fwd", "fxn_heads_bwd", "fxn_total_loss", "fxn_triplet_fwd", "fxn_triplet_bwd", "fxn_clip_adam_step",
     "fxn_split_planes_multi", "fxn_gather_rows", "fxn_reparam_fwd", "fxn_reparam_bwd", "fxn_row_sqnorm",
     "fxn_mmd_finish", "fxn_mmd_grad", "fxn_loss_weights", "fxn_randn", "fxn_gcn_fwd", "fxn_gcn_bwd",
     "fxn_merge_col_stats", "fxn_merge_col_stats_big", "fxn_graph_gather", "fxn_graph_gather_ok", "fxn_node_lin_fwd", "fxn_node_lin_bwd", "fxn_debug_gemm_trace", "fxn_debug_gemm_cta_times", "fxn_dp_reduce_sumsq", "fxn_dp_adam_bcast", "fxn_dp_barrier",
@@ -355,6 +357,17 @@ def heads_bwd(desc: HeadsDesc) -> None:
 def cox_fwd(o, ldo, durations, events, n, coef, acc) -> None:
     check(lib.fxn_cox_fwd(C.c_void_p(o), c_ll(ldo), C.c_void_p(durations), C.c_void_p(events), C.c_int(n),
                           C.c_void_p(coef), C.c_void_p(acc), C.c_void_p(stream())), "fxn_cox_fwd")
+
+
+def cox_fwd_ws(o, ldo, durations, events, n, coef, acc, workspace) -> None:
+    """whole-chip pairwise version, no row limit; workspace: cox_ws_floats(n) fp32, 8-byte aligned"""
+    check(lib.fxn_cox_fwd_ws(C.c_void_p(o), c_ll(ldo), C.c_void_p(durations), C.c_void_p(events), C.c_int(n),
+                             C.c_void_p(coef), C.c_void_p(acc), C.c_void_p(workspace), C.c_void_p(stream())), "fxn_cox_fwd_ws")
+
+
+def cox_ws_floats(n: int) -> int:
+    lib.fxn_cox_ws_floats.restype = c_ll
+    return int(lib.fxn_cox_ws_floats(C.c_int(n)))
 
 
 def cox_max_rows() -> int:

@@ -61,11 +61,15 @@ struct BnArgs {
   long long stat_rows;    // rows the statistics are taken over (= rows * fold)
   int pcols;              // number of real channels: the per-channel vectors have this length
   int period;             // 0, or pcols when `fold` consecutive rows of a contiguous narrow matrix are viewed as one row
+  uint8_t* keep_bits;     // optional: keep flags per run of 8 columns, index = the Philox element index
 };
 
 constexpr int BN_COLS = 64;     // columns per block (8 per thread x 8 threads)
 constexpr int BN_ROWS = 64;     // rows per block (2 per thread): many small blocks keep HBM requests in flight
 constexpr int BN_THREADS = 256;
+#ifndef BN_MIN_BLOCKS
+#define BN_MIN_BLOCKS 4          // 64 registers per thread: 32 warps per SM instead of 24 (the kernels are latency / issue bound)
+#endif
 
 // Rows per block: 64 keeps many small blocks (and HBM requests) in flight for the [4096 x 512]-sized activations of the
 // MLP encoders; tall inputs (flexGCN normalises B*N = 8 M rows of 32 channels) get fatter blocks so that the grid stays
@@ -97,7 +101,7 @@ __device__ __forceinline__ void merge_stats(const float* partials, int ntiles, i
   var = m2 / static_cast<float>(rows);
 }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_fwd_kernel(const BnArgs a) {
+__global__ void __launch_bounds__(BN_THREADS, BN_MIN_BLOCKS) bn_fwd_kernel(const BnArgs a) {
   __shared__ float s_scale[BN_COLS], s_shift[BN_COLS];
   __shared__ float s_red[4][BN_COLS];
   __shared__ float s_mean[BN_COLS];
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_fwd_kernel(const BnArgs a) {
         keep = dropout_keep8(step_seed(a.seed, a.seed_dev),
                              static_cast<unsigned long long>(r) * ((a.cols + 7) / 8) + (c >> 3), a.p_drop);
       }
+      if (a.keep_bits) a.keep_bits[static_cast<unsigned long long>(r) * ((a.cols + 7) / 8) + (c >> 3)] = static_cast<uint8_t>(keep);
     }
     float y[8];
 #pragma unroll
@@ -266,6 +271,7 @@ struct BnBwdArgs {
   int acc_affine;                       // dgamma/dbeta += (module applied several times per step)
   int rpb;                              // rows per block (multiple of 32)
   long long stat_rows; int pcols, period;   // see BnArgs
+  const uint8_t* keep_bits;                 // optional: flags stored by the forward pass (replaces mask / Philox)
 };
 
 // recompute g = dOut * dropout * act'(y) for 8 columns of row r; also returns xhat
@@ -276,7 +282,9 @@ __device__ __forceinline__ void bn_bwd_load(const BnBwdArgs& a, long long r, int
   const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
   uint32_t keep = 0xFFu;
   if (drop) {
-    if (a.mask) {
+    if (a.keep_bits) {
+      keep = a.keep_bits[static_cast<unsigned long long>(r) * ((a.cols + 7) / 8) + (c >> 3)];
+    } else if (a.mask) {
       keep = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -318,7 +326,7 @@ __device__ __forceinline__ void bn_bwd_load(const BnBwdArgs& a, long long r, int
   }
 }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnBwdArgs a) {
+__global__ void __launch_bounds__(BN_THREADS, BN_MIN_BLOCKS) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   __shared__ float s_mean[BN_COLS], s_rstd[BN_COLS], s_gamma[BN_COLS], s_beta[BN_COLS];
   __shared__ float s_acc[2][32][BN_COLS + 1];
   const int c0 = blockIdx.x * BN_COLS;
@@ -362,7 +370,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const BnBwdAr
   }
 }
 
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const BnBwdArgs a) {
+__global__ void __launch_bounds__(BN_THREADS, BN_MIN_BLOCKS) bn_bwd_apply_kernel(const BnBwdArgs a) {
   __shared__ float s_mean[BN_COLS], s_rstd[BN_COLS], s_gamma[BN_COLS], s_beta[BN_COLS], s_m1[BN_COLS], s_m2[BN_COLS];
   __shared__ float s_acc[32][BN_COLS + 1];
   const int c0 = blockIdx.x * BN_COLS;
@@ -496,6 +504,7 @@ extern "C" int fxn_bn_act_fwd(const fxn_bn_fwd_desc* d, void* stream_) {
   a.out = d->out; a.ldo = d->ldo;
   a.out_hi = static_cast<__nv_bfloat16*>(d->out_hi); a.out_lo = static_cast<__nv_bfloat16*>(d->out_lo); a.ldp = d->ldp;
   a.saved = d->saved;
+  a.keep_bits = d->keep_bits;
   a.stat_rows = d->stat_rows > 0 ? d->stat_rows : a.rows; a.pcols = a.cols; a.period = 0;
   {
     // fold narrow contiguous matrices into 64-wide rows (see chan())
@@ -530,6 +539,7 @@ extern "C" int fxn_bn_act_bwd(const fxn_bn_bwd_desc* d, void* stream_) {
   a.dv_hi = static_cast<__nv_bfloat16*>(d->dv_hi); a.dv_lo = static_cast<__nv_bfloat16*>(d->dv_lo); a.ldp = d->ldp;
   a.grad_scale = d->grad_scale == 0.f ? 1.f : d->grad_scale;
   a.acc_affine = d->accumulate_affine;
+  a.keep_bits = d->keep_bits;
   a.stat_rows = d->stat_rows > 0 ? d->stat_rows : a.rows; a.pcols = a.cols; a.period = 0;
   if (d->phase < 0 || d->phase > 2) return set_error(FXN_ERR_ARG, "fxn_bn_act_bwd: phase must be 0, 1 or 2");
   {

@@ -288,6 +288,113 @@ cox_kernel(const float* __restrict__ o, long long ldo, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cox partial likelihood on the whole chip: the same sums as cox_kernel without the sort. Row j is in the risk set of
+// row i iff it comes before-or-at i in the (duration descending, row index ascending) order, i.e.
+// before(j, i) = t_j > t_i || (t_j == t_i && j <= i); so S_i = sum_j before(j, i) exp(o_j) and, for the gradient,
+// R_b = sum over events i with before(b, i) of 1 / S_i. Both are [n x n] pairwise passes: a CTA owns 256 rows x 512
+// columns (columns staged in shared memory as (t, value) pairs and broadcast), partial row sums go out as fp32 atomics.
+// 16.7 M pairs at n = 4096 are a few microseconds on 128 CTAs, against ~100 us for the single-CTA bitonic sort + scans,
+// and there is no row limit. Rows with NaN duration / event are outside every sum.
+// ------------------------------------------------------------------------------------------------
+constexpr int CP_ROWS = 256, CP_COLS = 512;
+
+// ws: [S n][R n][events, nvalid][double num]
+template <int PASS>
+__global__ void __launch_bounds__(CP_ROWS)
+cox_pair_kernel(const float* __restrict__ o, long long ldo, const float* __restrict__ dur, const float* __restrict__ evt, int n,
+                float* __restrict__ ws) {
+  __shared__ float2 s_col[CP_COLS];
+  __shared__ double s_red[CP_ROWS / 32];
+  __shared__ float s_cnt[2][CP_ROWS / 32];
+  float* S = ws;
+  float* R = ws + n;
+  float* counts = ws + 2 * static_cast<size_t>(n);
+  double* num = reinterpret_cast<double*>(ws + 2 * static_cast<size_t>(n) + 2);
+  const int tid = threadIdx.x, j0 = blockIdx.y * CP_COLS;
+  for (int jj = tid; jj < CP_COLS; jj += CP_ROWS) {
+    const int j = j0 + jj;
+    float t = 0.f, v = 0.f;
+    if (j < n) {
+      const float tj = dur[j], ej = evt[j];
+      if (!isnan(tj) && !isnan(ej)) {
+        t = tj;
+        if (PASS == 1) v = expf(o[static_cast<long long>(j) * ldo]);
+        else v = ej == 1.f ? 1.f / S[j] : 0.f;
+      }
+    }
+    s_col[jj] = make_float2(t, v);          // rows outside the likelihood carry value 0
+  }
+  __syncthreads();
+  const int i = blockIdx.x * CP_ROWS + tid;
+  float ti = 0.f, ei = 0.f;
+  bool valid = false;
+  if (i < n) {
+    ti = dur[i]; ei = evt[i];
+    valid = !isnan(ti) && !isnan(ei);
+  }
+  float acc = 0.f;
+  if (valid) {
+    const int rel = i - j0;                 // tie rule on indices, relative to this column block
+#pragma unroll 8
+    for (int jj = 0; jj < CP_COLS; ++jj) {
+      const float2 c = s_col[jj];
+      bool in;
+      if (PASS == 1) in = (c.x > ti) || (c.x == ti && jj <= rel);      // before(j, i)
+      else in = (ti > c.x) || (ti == c.x && rel <= jj);                // before(i, j)
+      acc += in ? c.y : 0.f;
+    }
+    if (acc != 0.f) atomicAdd((PASS == 1 ? S : R) + i, acc);
+  }
+  if (blockIdx.y == 0) {                    // once per row block: the scalar sums
+    const int lane = tid & 31, warp = tid >> 5;
+    if (PASS == 1) {
+      float ev = valid ? ei : 0.f, nv = valid ? 1.f : 0.f;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) { ev += __shfl_xor_sync(0xffffffffu, ev, off); nv += __shfl_xor_sync(0xffffffffu, nv, off); }
+      if (lane == 0) { s_cnt[0][warp] = ev; s_cnt[1][warp] = nv; }
+      __syncthreads();
+      if (tid == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < CP_ROWS / 32; ++w) { a += s_cnt[0][w]; b += s_cnt[1][w]; }
+        atomicAdd(counts, a);
+        atomicAdd(counts + 1, b);
+      }
+    } else {
+      double t = 0.0;
+      if (valid && ei == 1.f) t = static_cast<double>(o[static_cast<long long>(i) * ldo]) - static_cast<double>(logf(S[i]));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+      if (lane == 0) s_red[warp] = t;
+      __syncthreads();
+      if (tid == 0) {
+        double a = 0.0;
+        for (int w = 0; w < CP_ROWS / 32; ++w) a += s_red[w];
+        atomicAdd(num, a);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cox_finish_kernel(const float* __restrict__ o, long long ldo, const float* __restrict__ dur, const float* __restrict__ evt,
+                  int n, const float* __restrict__ ws, float* __restrict__ coef, float* __restrict__ acc) {
+  const float* R = ws + n;
+  const float events = ws[2 * static_cast<size_t>(n)], nv = ws[2 * static_cast<size_t>(n) + 1];
+  const double num = *reinterpret_cast<const double*>(ws + 2 * static_cast<size_t>(n) + 2);
+  float loss = static_cast<float>(-num / static_cast<double>(events));
+  const bool ok = (nv > 0.f) && isfinite(loss);
+  if (!ok) loss = 0.f;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float t = dur[i], e = evt[i];
+    float c = 0.f;
+    if (ok && !isnan(t) && !isnan(e)) c = -((e == 1.f ? 1.f : 0.f) - expf(o[static_cast<long long>(i) * ldo]) * R[i]) / events;
+    coef[i] = c;
+  }
+  if (i == 0) { acc[0] = loss; acc[1] = 1.f; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // total loss (Kendall uncertainty weighting) + upstream weights for the backward pass
 // kinds[k]: 1 = mean of (sum, count) in acc[k]; 3 = value already in acc[k][0]
 // ------------------------------------------------------------------------------------------------
@@ -439,6 +546,26 @@ extern "C" int fxn_cox_fwd(const float* o, long long ldo, const float* durations
   }
   cox_kernel<<<1, COX_THREADS, smem, stream>>>(o, ldo, durations, events, n, npow2, coef, acc);
   FXN_CHECK_LAUNCH("cox");
+  return 0;
+}
+
+extern "C" long long fxn_cox_ws_floats(int n) { return 2LL * n + 4; }
+
+extern "C" int fxn_cox_fwd_ws(const float* o, long long ldo, const float* durations, const float* events, int n, float* coef,
+                              float* acc, float* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!o || !durations || !events || !coef || !acc || !workspace || n <= 0)
+    return set_error(FXN_ERR_ARG, "fxn_cox_fwd_ws: bad argument");
+  if (reinterpret_cast<uintptr_t>(workspace) & 7) return set_error(FXN_ERR_ARG, "fxn_cox_fwd_ws: workspace must be 8-byte aligned");
+  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(float) * static_cast<size_t>(fxn_cox_ws_floats(n)), stream);
+  if (e != cudaSuccess) return set_error(FXN_ERR_CUDA, "cox workspace memset: %s", cudaGetErrorString(e));
+  dim3 grid((n + CP_ROWS - 1) / CP_ROWS, (n + CP_COLS - 1) / CP_COLS);
+  cox_pair_kernel<1><<<grid, CP_ROWS, 0, stream>>>(o, ldo, durations, events, n, workspace);
+  FXN_CHECK_LAUNCH("cox_pair_1");
+  cox_pair_kernel<2><<<grid, CP_ROWS, 0, stream>>>(o, ldo, durations, events, n, workspace);
+  FXN_CHECK_LAUNCH("cox_pair_2");
+  cox_finish_kernel<<<(n + 255) / 256, 256, 0, stream>>>(o, ldo, durations, events, n, workspace, coef, acc);
+  FXN_CHECK_LAUNCH("cox_finish");
   return 0;
 }
 

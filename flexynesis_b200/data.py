@@ -228,3 +228,65 @@ class DeviceTripletBatcher:
             p, q = self.sample_indices(a)
             yy = {k: torch.index_select(v, 0, a, out=self._ybuf[k][:a.numel()]) for k, v in self.ann.items()}
             yield self._gather(0, a), self._gather(1, p), self._gather(2, q), yy
+
+
+# ----------------------------------------------------------------------------------------------------
+# on-disk matrices -> pinned host memory -> HBM
+# ----------------------------------------------------------------------------------------------------
+def load_matrix_npy(path: str, device="cuda", rows_per_chunk: int = 8192, dtype=torch.float32) -> torch.Tensor:
+    """A [samples x features] `.npy` matrix (what `numpy.save` writes; any float / integer dtype, C order) as a tensor on
+    `device`, without ever holding a second full copy on the host: the file is memory-mapped, and `rows_per_chunk` rows at
+    a time are converted into one of two PINNED staging buffers and copied to the device asynchronously, so that the
+    conversion of chunk i + 1 overlaps the DMA of chunk i.
+
+    The reference reads modality matrices through pandas (`DataImporter.read_data`, data.py:155-190) or h5py
+    (`H5DataImporter._read_h5_as_dataframe`, h5_dataloader.py:79-103: `/matrix` float32, samples as rows) into DataFrames
+    and converts to tensors later; the matrix layout is the same [samples x features] float32 as here. (h5py is not
+    installed in this image, so the HDF5 container itself is not read; `numpy.save(path, h5['matrix'][...])` converts.)"""
+    import numpy as np
+    arr = np.load(path, mmap_mode="r")
+    if arr.ndim != 2:
+        raise ValueError(f"{path}: expected a 2-D [samples x features] matrix, got shape {arr.shape}")
+    n, d = arr.shape
+    dev = torch.device(device)
+    out = torch.empty(n, d, dtype=dtype, device=dev)
+    if dev.type != "cuda":
+        for r0 in range(0, n, rows_per_chunk):
+            out[r0:r0 + rows_per_chunk] = torch.from_numpy(np.ascontiguousarray(arr[r0:r0 + rows_per_chunk])).to(dtype)
+        return out
+    rows = min(rows_per_chunk, max(n, 1))
+    stage = [torch.empty(rows, d, dtype=dtype).pin_memory() for _ in range(2)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    copy_stream = torch.cuda.Stream(device=dev)
+    for i, r0 in enumerate(range(0, n, rows)):
+        k, m = i % 2, min(rows, n - r0)
+        if i >= 2:
+            done[k].synchronize()                        # the DMA that last used this staging buffer has finished
+        stage[k][:m].copy_(torch.from_numpy(np.ascontiguousarray(arr[r0:r0 + m])))
+        with torch.cuda.stream(copy_stream):
+            out[r0:r0 + m].copy_(stage[k][:m], non_blocking=True)
+            done[k].record(copy_stream)
+    copy_stream.synchronize()
+    return out
+
+
+def dataset_from_npy(paths: Dict[str, str], ann: Dict[str, torch.Tensor], variable_types: Dict[str, str], device="cuda",
+                     samples: Optional[List[str]] = None, features: Optional[Dict[str, List[str]]] = None):
+    """MultiOmicDataset duck type (dat / ann / features / samples / variable_types, reference data.py:940-1000) whose
+    modality matrices come from `.npy` files via load_matrix_npy and stay resident on `device`."""
+    dat = {k: load_matrix_npy(p, device) for k, p in paths.items()}
+    n = {v.shape[0] for v in dat.values()}
+    if len(n) != 1:
+        raise ValueError(f"modalities disagree on the number of samples: { {k: v.shape[0] for k, v in dat.items()} }")
+    n = n.pop()
+    ds = SyntheticMultiOmicDataset.__new__(SyntheticMultiOmicDataset)
+    ds.dat = dat
+    ds.ann = {k: torch.as_tensor(v).to(device) for k, v in ann.items()}
+    for k, v in ds.ann.items():
+        if v.shape[0] != n:
+            raise ValueError(f"annotation {k!r} has {v.shape[0]} rows, the matrices have {n}")
+    ds.variable_types = dict(variable_types)
+    ds.samples = list(samples) if samples is not None else [f"s{i}" for i in range(n)]
+    ds.features = features if features is not None else {k: [f"{k}_{j}" for j in range(v.shape[1])] for k, v in dat.items()}
+    ds.label_mappings, ds.feature_ann = {}, {}
+    return ds

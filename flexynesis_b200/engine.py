@@ -407,19 +407,21 @@ class HeadsBlock:
             if with_loss and kind == 3:
                 sync = eng.sync
                 if sync is None:
-                    L.cox_fwd(ws["logits"][v].data_ptr(), 1, y[self.surv_time].data_ptr(), y[self.surv_event].data_ptr(),
-                              B, ws["coef"].data_ptr(), fptr(ws["acc"], 2 * slot))
+                    if "cox_ws" not in ws:
+                        ws["cox_ws"] = torch.zeros(L.cox_ws_floats(B) + 2, device=eng.device)
+                    L.cox_fwd_ws(ws["logits"][v].data_ptr(), 1, y[self.surv_time].data_ptr(), y[self.surv_event].data_ptr(),
+                                 B, ws["coef"].data_ptr(), fptr(ws["acc"], 2 * slot), ws["cox_ws"].data_ptr())
                 else:
                     # global risk sets: gather (o, t, e) of every rank, evaluate the partial likelihood on world * B rows,
                     # keep this rank's coefficients (x world: the gradient all-reduce averages over ranks)
                     n = sync.world * B
-                    if n > L.cox_max_rows():
-                        raise L.FxnError(f"global Cox batch of {n} rows exceeds the kernel limit {L.cox_max_rows()}")
                     og = sync.all_gather(ws["logits"][v].reshape(-1)).view(-1)
                     tg = sync.all_gather(y[self.surv_time].reshape(-1)).view(-1)
                     eg = sync.all_gather(y[self.surv_event].reshape(-1)).view(-1)
                     cg = torch.empty(n, device=eng.device)
-                    L.cox_fwd(og.data_ptr(), 1, tg.data_ptr(), eg.data_ptr(), n, cg.data_ptr(), fptr(ws["acc"], 2 * slot))
+                    cws = torch.zeros(L.cox_ws_floats(n) + 2, device=eng.device)
+                    L.cox_fwd_ws(og.data_ptr(), 1, tg.data_ptr(), eg.data_ptr(), n, cg.data_ptr(), fptr(ws["acc"], 2 * slot),
+                                 cws.data_ptr())
                     torch.mul(cg[sync.rank * B:(sync.rank + 1) * B], float(sync.world), out=ws["coef"])
         if with_loss and eng.sync is not None:
             # means over the valid labels of the GLOBAL batch: count_global / world replaces the local count
@@ -1405,6 +1407,9 @@ class GNNEngine(EngineBase):
             ws["dO_p"] = Planes.empty(rows, emb, dev)
             ws["tile_partials"] = f(L.stat_tiles(rows // fo) * 2 * fo * emb)
             ws["merge_scratch"] = torch.zeros(2 * emb, dtype=torch.float64, device=dev)
+            # dropout keep flags of the wide layers, 1 bit per activation: BatchNorm backward reads them instead of running
+            # Philox again in both of its passes (the BatchNorm kernels over [B * N x 32] are instruction-bound)
+            ws["keep"] = {k: torch.empty(rows * ((emb + 7) // 8), dtype=torch.uint8, device=dev) for k in self.gemm_layers}
             ws["bias_bd"] = f(self.fold * emb)
             ws["dW_bd"] = f(self.fold * emb, self.fold * emb)
         ws["x"] = None
@@ -1454,6 +1459,8 @@ class GNNEngine(EngineBase):
             else:
                 dst = ws["Dlast"] if last else ws["D"][k]
                 kw = dict(out=dst.data_ptr(), ldo=emb)
+            if train and k in self.gemm_layers and self.p_drop > 0:
+                kw["keep_bits"] = ws["keep"][k].data_ptr()
             self.bn_forward(V=ws["O"][k].data_ptr(), ldv=emb, rows=rows, cols=emb, partials=ws["merged"][k].data_ptr(), ntiles=1,
                      tile_rows=rows, gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
                      momentum=MOMENTUM, eps=EPS, train=int(train), act=self.act, p_drop=self.p_drop if train else 0.0,
@@ -1498,6 +1505,8 @@ class GNNEngine(EngineBase):
             gemm_path = k in self.gemm_layers
             out_kw = dict(dv_hi=ws["dO_p"].hi_ptr, dv_lo=ws["dO_p"].lo_ptr, ldp=emb, dbias=a.g(pb)) if gemm_path \
                 else dict(dV=ws["dO"].data_ptr(), ldd=emb)
+            if gemm_path and self.p_drop > 0:
+                out_kw["keep_bits"] = ws["keep"][k].data_ptr()
             self.bn_backward(V=ws["O"][k].data_ptr(), ldv=emb, dOut=ws["dD"].data_ptr(), ldg=emb, rows=rows, cols=emb,
                              gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
                              saved=ws["saved"][k].data_ptr(), act=self.act, p_drop=self.p_drop,

@@ -257,3 +257,50 @@ def merge_stat_records(records: torch.Tensor, rows_per_rank: int):
     d = records[:, 0] / n - mean
     m2 = (records[:, 1] + n * d * d).sum(0)
     return mean, m2 / (world * n)
+
+
+# ----------------------------------------------------------------------------------------------------
+# host placement: one process per GPU, on the CPU cores next to it
+# ----------------------------------------------------------------------------------------------------
+def parse_cpulist(text: str):
+    """'0-3,8,10-11' (the format of /sys/devices/system/node/node*/cpulist) -> [0, 1, 2, 3, 8, 10, 11]"""
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index: int):
+    """NUMA node of a CUDA device from sysfs (None when the platform does not say, e.g. single-socket boxes report -1)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index)
+        bdf = f"{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0"
+        with open(os.path.join("/sys/bus/pci/devices", bdf, "numa_node")) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def pin_to_gpu_numa_node(device_index: int):
+    """Restrict this process to the CPU cores of the NUMA node its GPU hangs off, so that the pinned staging buffers of the
+    host -> device batch path (fit.HostStreamTrainer, data.load_matrix_npy) are allocated and filled on the socket whose
+    PCIe root the DMA goes through. Returns the core list, or None when the topology is unknown (nothing is changed)."""
+    import os
+    node = gpu_numa_node(device_index)
+    if node is None:
+        return None
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None

@@ -151,6 +151,9 @@ typedef struct fxn_bn_fwd_desc {
   long long stat_rows;                       /* rows the batch statistics cover (0 = rows). Larger than `rows` when the
                                                 partials were gathered from several ranks (global-batch BatchNorm): the
                                                 tiles then describe stat_rows rows, this call normalises its own `rows` */
+  uint8_t* keep_bits;                        /* optional [rows * ceil(cols / 8)] bytes: the dropout keep flags of each run of 8
+                                                columns as drawn, so that the backward pass (fxn_bn_bwd_desc.keep_bits) reads
+                                                one byte instead of re-evaluating Philox twice; 1 bit per activation */
 } fxn_bn_fwd_desc;
 int fxn_bn_act_fwd(const fxn_bn_fwd_desc* d, void* stream);
 
@@ -174,6 +177,7 @@ typedef struct fxn_bn_bwd_desc {
   int phase;             /* 0: whole backward. 1: only the column reductions into `sums` (sum g, sum g*xhat over this
                             call's rows). 2: only the apply pass, reading `sums` as given -- a data-parallel caller
                             sum-all-reduces `sums` between phase 1 and phase 2 (SyncBN backward) */
+  const uint8_t* keep_bits; /* optional: the keep flags the forward call stored (replaces mask / Philox) */
 } fxn_bn_bwd_desc;
 int fxn_bn_act_bwd(const fxn_bn_bwd_desc* d, void* stream);
 
@@ -197,6 +201,13 @@ int fxn_head_out_bwd(const float* D, long long ldd, int rows, int sh, const floa
 int fxn_cox_fwd(const float* o, long long ldo, const float* durations, const float* events, int n, float* coef,
                 float* acc, void* stream);
 int fxn_cox_max_rows(void);
+/* The same loss and coefficients on the whole chip and without a row limit: pairwise passes instead of the single-CTA
+ * sort + scans (risk set of row i = rows j with t_j > t_i, or t_j == t_i and j <= i, which is the sorted order the
+ * reference's descending argsort + cumsum sees with ties kept in row order). workspace: fxn_cox_ws_floats(n) floats,
+ * 8-byte aligned, zeroed by the call. Sums are fp32 atomics (order varies between runs at the 1e-7 level). */
+long long fxn_cox_ws_floats(int n);
+int fxn_cox_fwd_ws(const float* o, long long ldo, const float* durations, const float* events, int n, float* coef,
+                   float* acc, float* workspace, void* stream);
 /* compute_total_loss (direct_pred.py:192-223). acc [n][2]; kinds[n] (device): 1 = mean of (sum, count), 3 = value in
  * acc[k][0]. out: [0,n) losses, [n] total, [n+1] unweighted sum (validation objective, :290), [n+2, 2n+2) weights
  * d total / d loss_k. With weighting and n > 1, *dlog_vars[k] = 1 - exp(-s_k) * loss_k. Pointer tables are device arrays. */

@@ -335,3 +335,48 @@ def test_validation_of_equal_size_cannot_alias_the_captured_training_batch():
     num = sum(float((out[0][k] - out[1][k]).double().pow(2).sum()) for k in keys)
     den = sum(float(out[0][k].double().pow(2).sum()) for k in keys)
     assert num <= (1e-3 ** 2) * den, (num / den) ** 0.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 37, 512, 4096, 20000])
+def test_cox_pairwise_matches_sort_kernel_and_torch(n):
+    """fxn_cox_fwd_ws (whole chip, pairwise passes, no row limit) against the single-CTA sort + scan kernel (n <= 16384) and
+    against torch's own argsort / cumsum formulation in float64, with tied durations, NaN rows and censored rows."""
+    from flexynesis_b200 import _lib as L
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(n)
+    o = torch.randn(n, generator=g)
+    t = torch.randint(0, max(n // 3, 2), (n,), generator=g).float()          # many ties
+    e = (torch.rand(n, generator=g) < 0.6).float()
+    if n > 8:
+        t[torch.randperm(n, generator=g)[: n // 10]] = float("nan")
+        e[torch.randperm(n, generator=g)[: n // 20]] = float("nan")
+    od, td, ed = o.to(dev), t.to(dev), e.to(dev)
+    coef, acc = torch.full((n,), 7.0, device=dev), torch.zeros(2, device=dev)
+    ws = torch.zeros(L.cox_ws_floats(n) + 2, device=dev)
+    L.cox_fwd_ws(od.data_ptr(), 1, td.data_ptr(), ed.data_ptr(), n, coef.data_ptr(), acc.data_ptr(), ws.data_ptr())
+    torch.cuda.synchronize()
+    # float64 reference: sorted order = (duration descending, row ascending) over the valid rows
+    valid = ~(torch.isnan(t) | torch.isnan(e))
+    idx = torch.nonzero(valid).flatten()
+    want_coef = torch.zeros(n, dtype=torch.float64)
+    want_loss = 0.0
+    if idx.numel() > 0 and float(e[idx].sum()) > 0:
+        order = sorted(idx.tolist(), key=lambda i: (-float(t[i]), i))
+        oo = o[order].double().requires_grad_(True)
+        ev = e[order].double()
+        S = torch.cumsum(torch.exp(oo), 0)
+        loss = -((oo - torch.log(S)) * (ev == 1)).sum() / ev.sum()
+        loss.backward()
+        want_loss = float(loss)
+        want_coef[order] = oo.grad
+    assert abs(float(acc[0]) - want_loss) <= 1e-5 * max(1.0, abs(want_loss)), (float(acc[0]), want_loss)
+    assert float(acc[1]) == 1.0
+    scale = max(float(want_coef.abs().max()), 1e-12)
+    assert float((coef.cpu().double() - want_coef).abs().max()) <= 1e-4 * scale
+    if n <= L.cox_max_rows():
+        coef1, acc1 = torch.zeros(n, device=dev), torch.zeros(2, device=dev)
+        L.cox_fwd(od.data_ptr(), 1, td.data_ptr(), ed.data_ptr(), n, coef1.data_ptr(), acc1.data_ptr())
+        torch.cuda.synchronize()
+        assert abs(float(acc1[0]) - float(acc[0])) <= 1e-5 * max(1.0, abs(want_loss))
+        assert float((coef1 - coef).abs().max()) <= 1e-4 * scale

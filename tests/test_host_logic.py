@@ -240,3 +240,41 @@ def test_predict_and_transform_formats_on_cpu():
         assert np.isfinite(emb.to_numpy()).all()
     dec = fx.CrossModalPred(cfg, ds, ["y"], input_layers=["l0"], output_layers=["l1"], device_type="cpu").decode(ds)
     assert set(dec) == {"l1"} and dec["l1"].shape == (30, 12) and list(dec["l1"].columns) == ds.samples
+
+
+def test_parse_cpulist_and_numa_helpers():
+    from flexynesis_b200.parallel import gpu_numa_node, parse_cpulist, pin_to_gpu_numa_node
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("") == []
+    assert parse_cpulist("5") == [5]
+    # without a GPU the topology is unknown and nothing is changed
+    import os
+    before = os.sched_getaffinity(0)
+    if not torch.cuda.is_available():
+        assert gpu_numa_node(0) is None and pin_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before or torch.cuda.is_available()
+
+
+def test_load_matrix_npy_roundtrip(tmp_path):
+    """on-disk matrix -> tensor (CPU route of the pinned-staging loader): values, dtype conversion, ragged last chunk,
+    and the MultiOmicDataset duck type built from files"""
+    import numpy as np
+    from flexynesis_b200.data import dataset_from_npy, load_matrix_npy
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((37, 11)).astype(np.float64)
+    b = rng.integers(0, 50, (37, 5)).astype(np.int32)
+    np.save(tmp_path / "a.npy", a)
+    np.save(tmp_path / "b.npy", b)
+    ta = load_matrix_npy(str(tmp_path / "a.npy"), "cpu", rows_per_chunk=8)
+    assert ta.dtype == torch.float32 and ta.shape == (37, 11)
+    assert torch.equal(ta, torch.from_numpy(a).float())
+    ds = dataset_from_npy({"rna": str(tmp_path / "a.npy"), "cnv": str(tmp_path / "b.npy")},
+                          {"y": torch.arange(37.0)}, {"y": "numerical"}, device="cpu")
+    assert len(ds) == 37 and list(ds.dat) == ["rna", "cnv"] and len(ds.features["cnv"]) == 5
+    x, y, name = ds[3]
+    assert torch.equal(x["cnv"], torch.from_numpy(b[3]).float()) and float(y["y"]) == 3.0 and name == "s3"
+    np.save(tmp_path / "c.npy", rng.standard_normal((5,)))
+    with pytest.raises(ValueError):
+        load_matrix_npy(str(tmp_path / "c.npy"), "cpu")
+    with pytest.raises(ValueError):
+        dataset_from_npy({"rna": str(tmp_path / "a.npy")}, {"y": torch.zeros(3)}, {"y": "numerical"}, device="cpu")
