@@ -10,6 +10,7 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
+import os
 import torch
 from torch import nn
 
@@ -406,7 +407,10 @@ class HeadsBlock:
                            fptr(ws["acc"], 2 * slot))
             if with_loss and kind == 3:
                 sync = eng.sync
-                if sync is None:
+                if sync is None and os.environ.get("FXN_COX_SORT") and B <= L.cox_max_rows():   # the single-CTA kernel (A/B switch)
+                    L.cox_fwd(ws["logits"][v].data_ptr(), 1, y[self.surv_time].data_ptr(), y[self.surv_event].data_ptr(),
+                              B, ws["coef"].data_ptr(), fptr(ws["acc"], 2 * slot))
+                elif sync is None:
                     if "cox_ws" not in ws:
                         ws["cox_ws"] = torch.zeros(L.cox_ws_floats(B) + 2, device=eng.device)
                     L.cox_fwd_ws(ws["logits"][v].data_ptr(), 1, y[self.surv_time].data_ptr(), y[self.surv_event].data_ptr(),
@@ -732,6 +736,8 @@ class TrunkEngine(EngineBase):
         mt = L.stat_tiles(Bp)
         ws["partials"] = [torch.zeros(G, mt * 2 * self.h[i], device=dev) for i in range(self.n)]
         ws["saved"] = [torch.zeros(G, 2 * self.h[i], device=dev) for i in range(self.n)]
+        # dropout keep flags as drawn by the forward pass (1 bit per activation), replayed by both BatchNorm backward passes
+        ws["keep"] = [torch.empty(G, B * ((self.h[i] + 7) // 8), dtype=torch.uint8, device=dev) for i in range(self.n)]
         ws["sums"] = [torch.zeros(G, 2 * self.h[i], device=dev) for i in range(self.n)]
         ws["Ecat"] = torch.zeros(R, self.n * self.Lp, device=dev)
         ws["Ecat_p"] = Planes.empty(R, self.n * self.Lp, dev, ld=self.n * self.Lp)
@@ -789,7 +795,7 @@ class TrunkEngine(EngineBase):
                            mask=None if mask is None else mask.data_ptr(), ldm=0 if mask is None else mask.stride(0),
                            seed=self.seed + 104729 * (i + 1) + 15485863 * g, seed_dev=self.noise_step.data_ptr(),
                            out_hi=D.hi_ptr, out_lo=D.lo_ptr, ldp=D.ld, saved=ws["saved"][i][g].data_ptr(),
-                           **_bn_ptrs(enc.batchnorm))
+                           keep_bits=ws["keep"][i][g].data_ptr() if train else None, **_bn_ptrs(enc.batchnorm))
               E_p = ws["Ecat_p"].cols_view(i * self.Lp, self.latent)
               bias2 = a.p(f"encoders.{i}.layer_out.bias") if enc.layer_out.bias is not None else None
               L.gemm(R, self.latent, h, ws["D"][i], 0, self.wp(self.w2[i]), 0, C_ptr=fptr(ws["Ecat"], i * self.Lp),
@@ -843,7 +849,8 @@ class TrunkEngine(EngineBase):
                                    dgamma=a.view(f"encoders.{i}.batchnorm.weight", a.grad),
                                    dbeta=a.view(f"encoders.{i}.batchnorm.bias", a.grad),
                                    accumulate_affine=0 if first else 1,   # affine grads add up over the three triplet passes
-                                   dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld, prezeroed=pz)
+                                   dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld, prezeroed=pz,
+                                   keep_bits=ws["keep"][i][g].data_ptr())
               self._aux_join(i)
         self._join()
         # dW1_i = dZ_i^T * X_i: the big weight gradients of all modalities start TOGETHER, each stream-K launch on its
@@ -1390,6 +1397,9 @@ class GNNEngine(EngineBase):
         ws["partials"] = [f(B, 2, emb) for _ in range(K)]
         ws["merged"] = [f(2, emb) for _ in range(K)]
         ws["saved"] = [f(2 * emb) for _ in range(K)]
+        # dropout keep flags as drawn by the forward pass, 1 bit per activation: BatchNorm backward reads them instead of
+        # running Philox again in both of its passes (the BatchNorm kernels over [B * N x 32] are instruction-bound)
+        ws["keep"] = [torch.empty(B * N * ((emb + 7) // 8), dtype=torch.uint8, device=dev) for _ in range(K)]
         ws["sums"] = [f(2 * emb) for _ in range(K)]
         ws["E"] = f(B, Lp)
         ws["E_p"] = Planes.empty(B, Lt, dev, ld=Lp)
@@ -1407,9 +1417,6 @@ class GNNEngine(EngineBase):
             ws["dO_p"] = Planes.empty(rows, emb, dev)
             ws["tile_partials"] = f(L.stat_tiles(rows // fo) * 2 * fo * emb)
             ws["merge_scratch"] = torch.zeros(2 * emb, dtype=torch.float64, device=dev)
-            # dropout keep flags of the wide layers, 1 bit per activation: BatchNorm backward reads them instead of running
-            # Philox again in both of its passes (the BatchNorm kernels over [B * N x 32] are instruction-bound)
-            ws["keep"] = {k: torch.empty(rows * ((emb + 7) // 8), dtype=torch.uint8, device=dev) for k in self.gemm_layers}
             ws["bias_bd"] = f(self.fold * emb)
             ws["dW_bd"] = f(self.fold * emb, self.fold * emb)
         ws["x"] = None
@@ -1459,7 +1466,7 @@ class GNNEngine(EngineBase):
             else:
                 dst = ws["Dlast"] if last else ws["D"][k]
                 kw = dict(out=dst.data_ptr(), ldo=emb)
-            if train and k in self.gemm_layers and self.p_drop > 0:
+            if train and self.p_drop > 0:
                 kw["keep_bits"] = ws["keep"][k].data_ptr()
             self.bn_forward(V=ws["O"][k].data_ptr(), ldv=emb, rows=rows, cols=emb, partials=ws["merged"][k].data_ptr(), ntiles=1,
                      tile_rows=rows, gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
@@ -1505,7 +1512,7 @@ class GNNEngine(EngineBase):
             gemm_path = k in self.gemm_layers
             out_kw = dict(dv_hi=ws["dO_p"].hi_ptr, dv_lo=ws["dO_p"].lo_ptr, ldp=emb, dbias=a.g(pb)) if gemm_path \
                 else dict(dV=ws["dO"].data_ptr(), ldd=emb)
-            if gemm_path and self.p_drop > 0:
+            if self.p_drop > 0:
                 out_kw["keep_bits"] = ws["keep"][k].data_ptr()
             self.bn_backward(V=ws["O"][k].data_ptr(), ldv=emb, dOut=ws["dD"].data_ptr(), ldg=emb, rows=rows, cols=emb,
                              gamma=a.p(f"encoders.0.bns.{k}.weight"), beta=a.p(f"encoders.0.bns.{k}.bias"),
