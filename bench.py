@@ -649,6 +649,9 @@ def run_b200(args, w):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from flexynesis_b200.parallel import pin_to_gpu_numa_node
+    all_cores = os.sched_getaffinity(0)                # (the CPU baseline leg below gets every core back)
+    pinned_cores = pin_to_gpu_numa_node(local)         # host threads + pinned staging buffers next to this rank's GPU
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its banner there)
@@ -739,6 +742,7 @@ def run_b200(args, w):
         w = dict(w, name=args.workload)
         roofline = roofline_gcn(model, w, dev, step.ws) if w["model"] == "GNN" else roofline_gemm(model, w, dev, step.ws)
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cores)
             threads = os.cpu_count() or 1
             sps, per, done = cpu_reference_steps(w, 20, 2, threads, budget_s=25.0)
             cpu_base = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "cpu": cpu_model_name(),
@@ -775,7 +779,9 @@ def run_b200(args, w):
                            "nvls": "; in the same graph: gradients reduce-scattered by multimem.ld_reduce, Adam on a 1/W slice "
                                    "per rank, parameters all-gathered by multimem.st, three in-stream multimem barriers "
                                    "(NVSwitch multicast, csrc/dp.cu)"}[dp_mode],
-                       "data_parallel": dp_mode, "data_parallel_note": dp_note},
+                       "data_parallel": dp_mode, "data_parallel_note": dp_note,
+                       "host_placement": (f"rank 0 restricted to the {len(pinned_cores)} cores of its GPU's NUMA node"
+                                          if pinned_cores else "GPU NUMA node not reported by sysfs: affinity unchanged")},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
             "gpu_launches": launches, "launches_per_step": step.launches_per_step,
