@@ -28,8 +28,11 @@ class GraphedStep:
         eng = model.engine(groups[0][0].device)
         self.eng = eng
         if eng.sync is not None:
-            raise NotImplementedError("global-batch sync (parallel.GlobalBatchSync) issues host-driven collectives between "
-                                      "kernels and runs eagerly: use model.fit_step, not a captured graph")
+            import torch.distributed as dist
+            if not (dist.is_initialized() and dist.get_backend(eng.sync.group) == "nccl"):
+                raise NotImplementedError("global-batch sync (parallel.GlobalBatchSync) inside a captured graph needs the NCCL "
+                                          "backend (its collectives are captured with the kernels); over gloo use "
+                                          "model.fit_step")
         lr = float(model.config["lr"] if lr is None else lr)
         eng.inputs.enabled = not resplit_inputs
         eng.ws_tag = f"graph{id(self)}"            # private workspace: eager calls of the same batch size cannot alias it

@@ -71,9 +71,38 @@ bn = max(float((a - b).abs().max()) for (ka, a), (kb, b) in zip(mA.named_buffers
 print(f"rank {rank}/{world}: loss {float(lossA):.6f} vs {float(eB.losses(wsB)['__total__']):.6f} (|d| {lerr:.2e}); "
       f"max grad diff / max grad {gerr:.2e}; logits diff {lg:.2e}; running-stat diff {bn:.2e}; collectives {eA.sync.calls}")
 ok = gerr < 2e-5 and lerr < 1e-5 and lg < 1e-4 and bn < 1e-5
+# the same sharded step captured in ONE CUDA graph (the NCCL collectives of GlobalBatchSync are captured with the kernels)
+# and replayed: its gradients must equal the eager step's
+gerr_graph = float("nan")
+try:
+    grad_eager = eA.arena.grad.clone()
+    mask_dev = {k: v[sl].to(dev).contiguous() for k, v in masks.items()}
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        eA.forward_backward(gA, yA, mask_dev)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize(); dist.barrier()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        eA.forward_backward(gA, yA, mask_dev)
+    torch.cuda.synchronize(); dist.barrier()
+    eA.arena.grad.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    gerr_graph = float((eA.arena.grad - grad_eager).abs().max()) / float(grad_eager.abs().max())
+    print(f"rank {rank}/{world}: captured step vs eager step: max grad diff / max grad {gerr_graph:.2e}")
+    ok = ok and gerr_graph < 2e-6
+    del graph                                            # (a live graph holding captured NCCL work stalls the teardown below)
+    torch.cuda.synchronize()
+except Exception as e:                                   # report, fail the check
+    print(f"rank {rank}/{world}: graph capture of the global-batch step failed: {type(e).__name__}: {e}")
+    ok = False
 flag = torch.tensor([int(ok)], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("GLOBAL BATCH CHECK OK" if int(flag) else "GLOBAL BATCH CHECK FAILED")
-dist.destroy_process_group()
-sys.exit(0 if int(flag) else 1)
+rc = 0 if int(flag) else 1
+sys.stdout.flush()
+dist.barrier()
+os._exit(rc)          # skip the process-group teardown: with captured NCCL collectives it waited until the launcher's timeout
