@@ -386,7 +386,8 @@ def roofline_gemm(model, w, dev, ws):
                     "algorithmic, issued_frac is what the tensor pipe executes",
             "avg_launch_us": avg_ms * 1e3, "algorithmic_bytes": 4.0 * (M * K + N * K + M * N),
             "traffic": measured_traffic(w.get("name", "")), "as_launched_in_step": in_step,
-            "ncu": {k: ev.get(k) for k in ("tensor_pipe_active_pct", "duration_us_under_ncu", "source")} if ev else None}
+            "ncu": {k: ev.get(k) for k in ("tensor_pipe_active_pct", "tensor_pipe_elapsed_pct", "grid_ctas", "duration_us_under_ncu",
+                                           "note", "source")} if ev else None}
 
 
 def roofline_gcn(model, w, dev, ws):
@@ -424,7 +425,7 @@ def roofline_gcn(model, w, dev, ws):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     nbytes = 4.0 * B * N * (fin + (fin if gemm_path else emb))
     achieved = nbytes / (avg_ms * 1e-3) / 1e9
-    kname = (f"graph_gather_kernel (GCN layer {k} aggregate A^ X: [B,N,{fin}] fp32 -> [B,N,{fin}] bf16 hi/lo planes; the linear map "
+    kname = (f"graph_gather_rows_kernel (GCN layer {k} aggregate A^ X: [B,N,{fin}] fp32 -> [B,N,{fin}] bf16 hi/lo planes; the linear map "
              "runs in fxn_gemm)") if gemm_path else f"gcn_fwd_kernel (GCN layer {k}: gather-aggregate + lin, [B,N,{fin}] -> [B,N,{emb}])"
     return {"bound": "hbm", "kernel": kname,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
