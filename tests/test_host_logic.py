@@ -278,3 +278,22 @@ def test_load_matrix_npy_roundtrip(tmp_path):
         load_matrix_npy(str(tmp_path / "c.npy"), "cpu")
     with pytest.raises(ValueError):
         dataset_from_npy({"rna": str(tmp_path / "a.npy")}, {"y": torch.zeros(3)}, {"y": "numerical"}, device="cpu")
+
+
+def test_reduce_scatter_context_claims_and_ranges():
+    """host bookkeeping of the GEMM-fused reduce-scatter (flexynesis_b200._lib.ReduceScatterContext): which outputs qualify
+    (contiguous, 16-byte aligned, 4-aligned length, inside the arena) and how the recorded ranges merge"""
+    from flexynesis_b200._lib import ReduceScatterContext
+    base, numel = 1 << 20, 10000
+    rs = ReduceScatterContext(world=4, rank=1, per=2500 - 2500 % 4, base_ptr=base, numel=numel, inbox_ptrs=[11, 22, 33, 44])
+    assert rs.claim(base + 4 * 128, 10, 20, 20) == 128                    # contiguous [10 x 20] at element 128
+    assert rs.claim(base + 4 * 128, 10, 20, 24) is None                   # ldc != N: rows are not contiguous
+    assert rs.claim(base + 4 * 129, 10, 20, 20) is None                   # not 16-byte aligned
+    assert rs.claim(base + 4 * 128, 3, 5, 5) is None                      # 15 elements: not a multiple of 4
+    assert rs.claim(base + 4 * 9990, 10, 20, 20) is None                  # runs past the end of the arena
+    assert rs.claim(base - 16, 2, 4, 4) is None                           # in front of the arena
+    rs.enabled = False
+    assert rs.claim(base + 4 * 128, 10, 20, 20) is None
+    rs.ranges.update({(0, 400), (400, 800), (1000, 1200), (1100, 1600)})
+    assert rs.merged_ranges() == [[0, 800], [1000, 1600]]
+    assert [int(p) for p in rs.inbox] == [11, 22, 33, 44]
