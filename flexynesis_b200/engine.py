@@ -714,6 +714,8 @@ class TrunkEngine(EngineBase):
         self._finish_init(self.n - 1)
         # stream-K fix-up workspaces of the first-layer GEMMs (one per modality branch: the branches overlap in time)
         self.fix = [L.FixWorkspace(self.device) for _ in range(self.n)]
+        # experiment switch: 1 = plain bf16 operands for the first-layer GEMMs (fails the 1e-3 parity bar)
+        self.l1_nterms = int(os.environ.get("FXN_L1_NTERMS", "3"))
         self.wgrad_groups = split_groups_tiles([((self.h[i] + 255) // 256) * ((self.d[i] + 127) // 128) for i in range(self.n)])
 
     def wf_planes(self, i: Optional[int] = None) -> Planes:
@@ -781,7 +783,8 @@ class TrunkEngine(EngineBase):
               L.gemm(R, h, self.d[i], ws["X"][i], 0, self.wp(self.w1[i]), 0, C_ptr=ws["Z"][i].data_ptr(), ldc=hp,
                      bias=a.p(f"encoders.{i}.layer_1.bias"),
                      colstats=ws["partials"][i].data_ptr() if use_epi_stats else None, stats_mode=2,
-                     block_n=plan[i][0], max_groups=plan[i][1], fix=self.fix[i] if self.n == 1 else None)
+                     block_n=plan[i][0], max_groups=plan[i][1], fix=self.fix[i] if self.n == 1 else None,
+                     nterms=self.l1_nterms)
               for g in range(G):
                   r0 = g * Bp
                   if train and G > 1:
@@ -859,7 +862,8 @@ class TrunkEngine(EngineBase):
         for i in range(self.n):
             with torch.cuda.stream(self._stream_for(i)):
                 L.gemm(self.h[i], self.d[i], R, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.layer_1.weight"),
-                       ldc=self.d[i], splitk=-1, prezeroed=pz, max_groups=self.wgrad_groups[i] if self.parallel_encoders else 0)
+                       ldc=self.d[i], splitk=-1, prezeroed=pz, max_groups=self.wgrad_groups[i] if self.parallel_encoders else 0,
+                       nterms=self.l1_nterms)
         self._join()
         self._aux_join(len(self.aux) - 1)          # the heads' weight gradients
 
