@@ -1086,6 +1086,11 @@ class VAEEngine(EngineBase):
         ws["cs_zz"], ws["cs_tz"], ws["cs_tt"] = f(B), f(nd, B), f(nd, P)
         ws["KT"] = f(nd, B, Lp)
         ws["heads"] = self.heads.workspace(B)
+        # accumulation scratch zeroed ONCE per training step together with the gradient arena (forward_backward): every
+        # stream-K output, column-sum bias gradient and BatchNorm reduction then runs without its own memset node (the
+        # captured config-3 step had 40 of them, each ~4 us of serialisation on the chain it sat in)
+        ws["_zero"] = list(ws["sums"]) + list(ws["sumsd"]) + [ws["cs_zz"], ws["cs_tz"], ws["cs_tt"], ws["heads"]["sums"],
+                                                               ws["heads"]["hf_sums"]]
         self.ws[key] = ws
         return ws
 
@@ -1115,7 +1120,7 @@ class VAEEngine(EngineBase):
                  p_drop=0.0, out_hi=Y.hi_ptr, out_lo=Y.lo_ptr, ldp=Y.ld, saved=ws["saved" + tag][i].data_ptr(),
                  **_bn_ptrs(bn))
 
-    def _hidden_bwd(self, ws, tag: str, i: int, prefix: str):
+    def _hidden_bwd(self, ws, tag: str, i: int, prefix: str, pz: bool = False):
         """BatchNorm backward + LeakyReLU derivative: dY (fp32) -> dZ planes; fills d gamma / beta / bias."""
         a = self.arena
         hh = self.hd if tag == "d" else self.h
@@ -1126,10 +1131,12 @@ class VAEEngine(EngineBase):
                          saved=ws["saved" + tag][i].data_ptr(), act=0, p_drop=0.0, pre_act=1,
                          sums=ws["sums" + tag][i], dgamma=a.view(f"{prefix}.hidden_layers.2.weight", a.grad),
                          dbeta=a.view(f"{prefix}.hidden_layers.2.bias", a.grad),
-                         dbias=a.g(f"{prefix}.hidden_layers.0.bias"), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld)
+                         dbias=a.g(f"{prefix}.hidden_layers.0.bias"), dv_hi=dz.hi_ptr, dv_lo=dz.lo_ptr, ldp=dz.ld,
+                         prezeroed=pz)
 
     # ---- forward: encoders -> latent -> decoders | heads | MMD ----
-    def _forward(self, ws, y, train: bool, noise, with_loss: bool, want_xhat: bool = False, backward: bool = False):
+    def _forward(self, ws, y, train: bool, noise, with_loss: bool, want_xhat: bool = False, backward: bool = False,
+                 pz: bool = False):
         a, hw = self.arena, ws["heads"]
         B, n, nd, Lt, Lp, P = ws["B"], self.ne, self.nd, self.latent, self.Lp, self.PRIOR
         noise = noise or {}
@@ -1164,10 +1171,11 @@ class VAEEngine(EngineBase):
         # ahead, the short chain runs on a few SMs while the GEMM's CTA pairs fill the others as they become free.
         self._fork()
         with torch.cuda.stream(self._aux_stream()):          # heads (incl. the single-CTA Cox sort, ~0.1 ms at B = 4096)
-            self.heads.forward(hw, ws["z_p"], B, y, train, noise, with_loss=with_loss, F32=ws["z"], backward=backward)
+            self.heads.forward(hw, ws["z_p"], B, y, train, noise, with_loss=with_loss, F32=ws["z"], backward=backward,
+                               prezeroed=pz)
         if with_loss:
             with torch.cuda.stream(self._mmd_stream()):      # Gram GEMMs of the MMD term: independent of the heads
-                self._mmd_forward(ws, train, noise)
+                self._mmd_forward(ws, train, noise, pz)
         for i in range(nd):
             with torch.cuda.stream(self._stream_for(i)):
                 self._hidden_fwd(ws, "d", i, f"decoders.{i}", ws["z_p"], Lt, self.wp(self.wd[i]), train)
@@ -1180,14 +1188,14 @@ class VAEEngine(EngineBase):
                        bias=a.p(f"decoders.{i}.FC_output.bias"), epi_act=3, out=ws["G"][i],
                        mse_x=x.data_ptr(), ldx=x.stride(0), mse_acc=fptr(ws["mse_acc"], i),
                        colstats=a.g(f"decoders.{i}.FC_output.bias") if train else None, stats_mode=3,
-                       stats_alpha=scale, stats_alpha_dev=w_mmd)
+                       stats_alpha=scale, stats_alpha_dev=w_mmd, prezeroed=pz)
         self._join()
         if with_loss:
             L.mmd_finish(ws["cs_zz"].data_ptr(), ws["cs_tt"].data_ptr(), ws["cs_tz"].data_ptr(),
                          ws["mse_acc"].data_ptr(), self.dims_dev.data_ptr(), nd, B, P, fptr(hw["acc"], 2 * self.mmd_slot))
             hb.total(hw)
 
-    def _mmd_forward(self, ws, train, noise):
+    def _mmd_forward(self, ws, train, noise, pz: bool = False):
         a = self.arena
         B, n, Lt, Lp, P = ws["B"], self.nd, self.latent, self.Lp, self.PRIOR      # n: decoded layers
         # MMD: Gaussian-kernel Gram matrices + column sums
@@ -1195,7 +1203,7 @@ class VAEEngine(EngineBase):
         nt = self.gram_nterms
         L.row_sqnorm(ws["z"].data_ptr(), Lp, B, Lt, ws["rz"].data_ptr())
         L.gemm(B, B, Lt, ws["z_p"], 0, ws["z_p"], 0, out=ws["Kzz_p"], epi_act=7, gauss_ra=ws["rz"].data_ptr(),
-               gauss_rb=ws["rz"].data_ptr(), gauss_inv=inv, colstats=ws["cs_zz"].data_ptr(), stats_mode=3, nterms=nt)
+               gauss_rb=ws["rz"].data_ptr(), gauss_inv=inv, colstats=ws["cs_zz"].data_ptr(), stats_mode=3, nterms=nt, prezeroed=pz)
         for i in range(n):
             T = ws["T"][i]
             if f"mmd_prior.{i}" in noise:
@@ -1206,10 +1214,10 @@ class VAEEngine(EngineBase):
             L.row_sqnorm(T.data_ptr(), Lp, P, Lt, ws["rt"][i].data_ptr())
             L.gemm(P, B, Lt, ws["T_p"][i], 0, ws["z_p"], 0, out=ws["Ktz_p"][i], epi_act=7,
                    gauss_ra=ws["rt"][i].data_ptr(), gauss_rb=ws["rz"].data_ptr(), gauss_inv=inv,
-                   colstats=ws["cs_tz"][i].data_ptr(), stats_mode=3, nterms=nt)
+                   colstats=ws["cs_tz"][i].data_ptr(), stats_mode=3, nterms=nt, prezeroed=pz)
             L.gemm(P, P, Lt, ws["T_p"][i], 0, ws["T_p"][i], 0, out=ws["Ktt_p"], epi_act=7,
                    gauss_ra=ws["rt"][i].data_ptr(), gauss_rb=ws["rt"][i].data_ptr(), gauss_inv=inv,
-                   colstats=ws["cs_tt"][i].data_ptr(), stats_mode=3, nterms=nt)
+                   colstats=ws["cs_tt"][i].data_ptr(), stats_mode=3, nterms=nt, prezeroed=pz)
 
     def forward_backward(self, x_groups, y, masks=None):
         x_list = x_groups[0]
@@ -1222,10 +1230,14 @@ class VAEEngine(EngineBase):
         self.ensure_fresh()
         self.noise_step.add_(1)                 # fresh epsilon / MMD prior / dropout for this pass
         self.stage_inputs(ws, x_list, targets)
-        self._forward(ws, y, True, masks, True, backward=True)
+        pz = self.sync is None
+        if pz:          # one fill of the gradient arena + one of the accumulation scratch instead of a memset in front of
+            a.grad.zero_()                                                    # every kernel that accumulates
+            torch._foreach_zero_(ws["_zero"])
+        self._forward(ws, y, True, masks, True, backward=True, pz=pz)
         w_mmd = fptr(ws["wts"], self.mmd_slot)
         # ---- backward ----
-        if not self.heads.backward(hw, ws["z_p"], B, y, masks, None, ws["dz"], None):
+        if not self.heads.backward(hw, ws["z_p"], B, y, masks, None, ws["dz"], None, prezeroed=pz):
             ws["dz"].zero_()
         self._fork()
         for i in range(nd):
@@ -1236,10 +1248,10 @@ class VAEEngine(EngineBase):
                 L.gemm(B, h, d, ws["G"][i], 0, self.wp(self.wo[i]), 1, C_ptr=ws["dYd"][i].data_ptr(), ldc=hp,
                        alpha=scale, alpha_dev=w_mmd)
                 L.gemm(d, h, B, ws["G"][i], 1, ws["Yd"][i], 1, C_ptr=a.g(f"decoders.{i}.FC_output.weight"), ldc=h,
-                       alpha=scale, alpha_dev=w_mmd, splitk=-1)
-                self._hidden_bwd(ws, "d", i, f"decoders.{i}")
+                       alpha=scale, alpha_dev=w_mmd, splitk=-1, prezeroed=pz)
+                self._hidden_bwd(ws, "d", i, f"decoders.{i}", pz)
                 L.gemm(h, Lt, B, ws["dZd"][i], 1, ws["z_p"], 1, C_ptr=a.g(f"decoders.{i}.hidden_layers.0.weight"),
-                       ldc=Lt, splitk=-1)
+                       ldc=Lt, splitk=-1, prezeroed=pz)
         with torch.cuda.stream(self._aux_stream()):      # MMD gradient operands beside the decoder chains
             L.gemm(B, Lt, B, ws["Kzz_p"], 0, ws["z_p"], 1, C_ptr=ws["KZ"].data_ptr(), ldc=Lp)
             for i in range(nd):
@@ -1261,18 +1273,18 @@ class VAEEngine(EngineBase):
                         ("FC_log_var", ws["ds_p"], ws["Vcat_p"], ws["dV_p"][i], self.wv[i], "FC_var")):
                     # d W_fc[:, iL:(i+1)L] = dsrc^T * cat_i
                     L.gemm(Lt, Lt, B, dsrc, 1, cat.cols_view(i * Lp, Lt), 1,
-                           C_ptr=fptr(a.grad, a.offset[f"{name}.weight"] + i * Lt), ldc=n * Lt, splitk=-1)
+                           C_ptr=fptr(a.grad, a.offset[f"{name}.weight"] + i * Lt), ldc=n * Lt, splitk=-1, prezeroed=pz)
                     # d cat_i = dsrc * W_fc[:, iL:(i+1)L]   (+ column sums -> bias gradient of the encoder's FC)
                     L.gemm(B, Lt, Lt, dsrc, 0, self.wfc(name, i), 1, out=dst,
-                           colstats=a.g(f"encoders.{i}.{encname}.bias"), stats_mode=3)
+                           colstats=a.g(f"encoders.{i}.{encname}.bias"), stats_mode=3, prezeroed=pz)
                     # dY_i (+)= d cat_i * W_enc ; d W_enc = d cat_i^T * Y_i
                     L.gemm(B, h, Lt, dst, 0, self.wp(wenc), 1, C_ptr=ws["dY"][i].data_ptr(), ldc=hp,
                            accumulate=(name != "FC_mean"))
                     L.gemm(Lt, h, B, dst, 1, ws["Y"][i], 1, C_ptr=a.g(f"encoders.{i}.{encname}.weight"), ldc=h,
-                           splitk=-1)
-                self._hidden_bwd(ws, "", i, f"encoders.{i}")
+                           splitk=-1, prezeroed=pz)
+                self._hidden_bwd(ws, "", i, f"encoders.{i}", pz)
                 L.gemm(h, d, B, ws["dZ"][i], 1, ws["X"][i], 1, C_ptr=a.g(f"encoders.{i}.hidden_layers.0.weight"),
-                       ldc=d, splitk=-1)
+                       ldc=d, splitk=-1, prezeroed=pz)
         self._join()
         self._aux_join(len(self.aux) - 1)          # the heads' weight gradients
         return ws
