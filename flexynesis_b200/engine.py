@@ -132,7 +132,7 @@ class ParamArena:
         self.exp_avg = torch.zeros(self.numel, dtype=torch.float32, device=device)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step = torch.zeros(1, dtype=torch.int64, device=device)
-        self.sumsq = torch.zeros(1, dtype=torch.float64, device=device)
+        self.sumsq = torch.zeros(2, dtype=torch.float64, device=device)      # norm scratch: {double sum, u32 counter}
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=device)
         with torch.no_grad():
             for name in self.names:

@@ -343,7 +343,8 @@ int fxn_merge_col_stats_big(const float* partials, int ntiles, int tile_rows, lo
 /* ---- step policy ----
  * clip_grad_norm_(params, max_norm) + Adam on flat arenas (flexynesis/main.py:216-217, direct_pred.py:135-144).
  * grads are multiplied by grad_scale (1/world_size after a sum all-reduce) before the norm. *step_counter (int64)
- * is incremented by the call; norm_out (optional) receives the pre-clip norm. */
+ * is incremented by the call; norm_out (optional) receives the pre-clip norm. sumsq_scratch: 16 bytes (a double and a
+ * 32-bit counter), zeroed ONCE by the caller; the call hands it back zeroed (no memset is queued per step). */
 int fxn_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                        float beta1, float beta2, float eps, float max_norm, float grad_scale, double* sumsq_scratch,
                        long long* step_counter, float* norm_out, void* stream);
