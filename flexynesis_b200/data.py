@@ -252,7 +252,7 @@ def load_matrix_npy(path: str, device="cuda", rows_per_chunk: int = 8192, dtype=
     out = torch.empty(n, d, dtype=dtype, device=dev)
     if dev.type != "cuda":
         for r0 in range(0, n, rows_per_chunk):
-            out[r0:r0 + rows_per_chunk] = torch.from_numpy(np.ascontiguousarray(arr[r0:r0 + rows_per_chunk])).to(dtype)
+            out[r0:r0 + rows_per_chunk] = torch.from_numpy(np.array(arr[r0:r0 + rows_per_chunk])).to(dtype)
         return out
     rows = min(rows_per_chunk, max(n, 1))
     stage = [torch.empty(rows, d, dtype=dtype).pin_memory() for _ in range(2)]
@@ -262,7 +262,7 @@ def load_matrix_npy(path: str, device="cuda", rows_per_chunk: int = 8192, dtype=
         k, m = i % 2, min(rows, n - r0)
         if i >= 2:
             done[k].synchronize()                        # the DMA that last used this staging buffer has finished
-        stage[k][:m].copy_(torch.from_numpy(np.ascontiguousarray(arr[r0:r0 + m])))
+        stage[k][:m].numpy()[...] = arr[r0:r0 + m]      # numpy converts straight from the mapped file into pinned memory
         with torch.cuda.stream(copy_stream):
             out[r0:r0 + m].copy_(stage[k][:m], non_blocking=True)
             done[k].record(copy_stream)
@@ -273,7 +273,8 @@ def load_matrix_npy(path: str, device="cuda", rows_per_chunk: int = 8192, dtype=
 def dataset_from_npy(paths: Dict[str, str], ann: Dict[str, torch.Tensor], variable_types: Dict[str, str], device="cuda",
                      samples: Optional[List[str]] = None, features: Optional[Dict[str, List[str]]] = None):
     """MultiOmicDataset duck type (dat / ann / features / samples / variable_types, reference data.py:940-1000) whose
-    modality matrices come from `.npy` files via load_matrix_npy and stay resident on `device`."""
+    modality matrices come from `.npy` files via load_matrix_npy and stay resident on `device` (DeviceBatcher's `.to(device)`
+    is then a no-op: the matrices are never copied again)."""
     dat = {k: load_matrix_npy(p, device) for k, p in paths.items()}
     n = {v.shape[0] for v in dat.values()}
     if len(n) != 1:
@@ -281,7 +282,8 @@ def dataset_from_npy(paths: Dict[str, str], ann: Dict[str, torch.Tensor], variab
     n = n.pop()
     ds = SyntheticMultiOmicDataset.__new__(SyntheticMultiOmicDataset)
     ds.dat = dat
-    ds.ann = {k: torch.as_tensor(v).to(device) for k, v in ann.items()}
+    ds.ann = {k: torch.as_tensor(v).cpu() for k, v in ann.items()}     # labels stay on the host (the constructors count classes
+                                                                         # with numpy); the batchers move them to the device
     for k, v in ds.ann.items():
         if v.shape[0] != n:
             raise ValueError(f"annotation {k!r} has {v.shape[0]} rows, the matrices have {n}")

@@ -380,3 +380,26 @@ def test_cox_pairwise_matches_sort_kernel_and_torch(n):
         torch.cuda.synchronize()
         assert abs(float(acc1[0]) - float(acc[0])) <= 1e-5 * max(1.0, abs(want_loss))
         assert float((coef1 - coef).abs().max()) <= 1e-4 * scale
+
+
+@pytest.mark.gpu
+def test_load_matrix_npy_through_pinned_staging(tmp_path):
+    """the CUDA route of data.load_matrix_npy: memory-mapped file -> two pinned staging buffers -> HBM, several chunks with a
+    ragged tail and a dtype conversion; the dataset built from the files trains one step"""
+    import numpy as np
+    from flexynesis_b200.data import dataset_from_npy, load_matrix_npy
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((1000, 257)).astype(np.float64)
+    np.save(tmp_path / "a.npy", a)
+    t = load_matrix_npy(str(tmp_path / "a.npy"), "cuda", rows_per_chunk=96)
+    assert t.is_cuda and t.dtype == torch.float32 and t.shape == (1000, 257)
+    assert torch.equal(t.cpu(), torch.from_numpy(a).float())
+    b = rng.standard_normal((1000, 64)).astype(np.float32)
+    np.save(tmp_path / "b.npy", b)
+    y = torch.from_numpy(rng.standard_normal(1000).astype(np.float32))
+    ds = dataset_from_npy({"rna": str(tmp_path / "a.npy"), "cnv": str(tmp_path / "b.npy")}, {"y": y}, {"y": "numerical"})
+    import flexynesis_b200 as fx
+    cfg = {"latent_dim": 32, "hidden_dim_factor": 0.25, "supervisor_hidden_dim": 16, "lr": 1e-3}
+    model = fx.DirectPred(cfg, ds, ["y"], device_type="gpu").to("cuda")
+    hist = fx.fit.fit(model, ds, batch_size=250, epochs=2, device="cuda")
+    assert len(hist) == 2 and all(np.isfinite(h["train_loss"]) for h in hist)
