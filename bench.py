@@ -730,7 +730,10 @@ def run_b200(args, w):
     also = {}
     if not args.quick:
         if args.workload != "cfg5":
-            also["cfg5"] = secondary_workload("cfg5", args, world, rank, local, dev)
+            try:
+                also["cfg5"] = secondary_workload("cfg5", args, world, rank, local, dev)
+            except Exception as e:                      # never lose the bench line over a secondary record
+                also["cfg5"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         if world == 1 and w["model"] == "DirectPred":
             try:
                 also.update(minibatch_records(w, dev))
