@@ -717,6 +717,8 @@ class TrunkEngine(EngineBase):
         # experiment switch: 1 = plain bf16 operands for the first-layer GEMMs (fails the 1e-3 parity bar)
         self.l1_nterms = int(os.environ.get("FXN_L1_NTERMS", "3"))
         self.wgrad_groups = split_groups_tiles([((self.h[i] + 255) // 256) * ((self.d[i] + 127) // 128) for i in range(self.n)])
+        if os.environ.get("FXN_WGRAD_SPLIT"):      # experiment switch: CTA pairs per first-layer weight gradient, e.g. "40,34"
+            self.wgrad_groups = [int(v) for v in os.environ["FXN_WGRAD_SPLIT"].split(",")][:self.n]
 
     def wf_planes(self, i: Optional[int] = None) -> Planes:
         full = self.wplanes.planes(self.wf_off, self.latent, self.n * self.Lp, self.n * self.Lp)
